@@ -1,0 +1,92 @@
+/*
+ * seunet_b200 - C ABI of the B200-native (sm_100a) SE-UNet forward/backward hot path.
+ *
+ * The reference (Beryl2000/SE-UNet-AirSeg) has no FFI layer: its boundary for this path is the
+ * Python nn.Module API of SE_UNet.py.  This header is the thin C ABI that the drop-in module
+ * (se_unet_airseg_b200/SE_UNet.py) binds with ctypes.  Each entry point names the reference
+ * interface it replaces.  Conventions:
+ *   - plain pointers and sizes only, no torch types; all pointers are DEVICE pointers unless noted;
+ *   - the caller owns all memory (parameters, workspace, inputs, outputs); nothing is allocated,
+ *     synchronised or called back inside; work is enqueued on the given CUDA stream;
+ *   - every function returns 0 on success, non-zero on error; seunet_last_error() then returns a
+ *     thread-local message;
+ *   - re-entrant per plan: one plan per (device, shape); no global mutable state.
+ */
+#ifndef SEUNET_B200_H
+#define SEUNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct seunet_plan seunet_plan_t;
+typedef void* seunet_stream_t; /* cudaStream_t */
+
+/* Library identity. act_dtype: 0 = fp16 storage/operands (default build), 1 = bf16. */
+int seunet_version(void);
+int seunet_act_dtype(void);
+const char* seunet_last_error(void);
+
+/* ---- parameters ---------------------------------------------------------------------------
+ * Parameters are ONE flat fp32 device buffer holding the 117 tensors of SE_UNet.state_dict()
+ * in registration order (SE_UNet.py:108-153), each in its native
+ * (Cout,Cin,kD,kH,kW) layout.  Gradients use the same flat layout. */
+int64_t seunet_param_count(int in_channel, int n_classes);
+/* Offset (in floats) of a named tensor, e.g. "dc5.conv1.weight"; -1 if unknown. */
+int64_t seunet_param_offset(int in_channel, int n_classes, const char* name);
+/* Number of tensors and, for index i, its name / element count (to cross-check against state_dict). */
+int seunet_param_tensors(int in_channel, int n_classes);
+const char* seunet_param_name(int in_channel, int n_classes, int i);
+int64_t seunet_param_numel(int in_channel, int n_classes, int i);
+
+/* ---- plan ---------------------------------------------------------------------------------
+ * A plan fixes (batch, D, H, W, in_channel, mode) and owns the launch descriptors (TMA tensor
+ * maps, tile geometry) for every layer of SE_UNet.forward (SE_UNet.py:181-238).
+ * mode: 0 = inference (conv scratch shared per resolution), 1 = training (activations kept
+ * for seunet_backward). */
+int seunet_plan_create(seunet_plan_t** plan, int batch, int D, int H, int W, int in_channel, int n_classes,
+                       int mode, int device);
+void seunet_plan_destroy(seunet_plan_t* plan);
+size_t seunet_plan_workspace_bytes(const seunet_plan_t* plan);
+/* Bytes of the packed tensor-core weight image (depends only on in_channel). */
+size_t seunet_plan_wimg_bytes(const seunet_plan_t* plan);
+/* Bind the plan to a caller-owned workspace + weight image (both 256-byte aligned). */
+int seunet_plan_bind(seunet_plan_t* plan, void* workspace, void* wimg, seunet_stream_t stream);
+
+/* Re-pack the fp32 parameters into the tensor-core weight image (call after every parameter
+ * update; replaces cuDNN's per-call filter transforms). */
+int seunet_pack_weights(seunet_plan_t* plan, const float* params, seunet_stream_t stream);
+
+/* SE_UNet.forward (SE_UNet.py:181-238).
+ *   x        fp32, element strides x_strides[5] = (n, c, d, h, w)  (callers pass non-contiguous
+ *            slices, prediction.py:102)
+ *   params   flat fp32 parameter buffer (see above)
+ *   drop0/1  DropLayer scale factors r*C/(sum r + 0.01) of shape [batch][24] / [batch][12]
+ *            (SE_UNet.py:89-97; all ones in eval mode) - drawn by the host module with the
+ *            reference's CPU-generator semantics
+ *   pred0/1  fp32 logits [batch][1][D][H][W], contiguous */
+int seunet_forward(seunet_plan_t* plan, const float* x, const int64_t* x_strides, const float* params,
+                   const float* drop0, const float* drop1, float* pred0, float* pred1, seunet_stream_t stream);
+
+/* ---- single-op entry points (parity tests and micro-benchmarks) --------------------------- */
+/* nn.Conv3d(Cin,Cout,k,padding=dil,dilation=dil) forward on chunk-plane activations
+ * (SE_UNet.py:15,42,57).  in: [N][in_chunks][D][H][W][8] storage type; w: fp32 (Cout,Cin,k,k,k);
+ * out: raw conv output [N][COUT/8][D][H][W][8]; stats: [N][COUT][2] fp64 (sum, sum sq), zeroed by
+ * the call. scratch must hold seunet_conv_scratch_bytes(). COUT = Cout rounded up to 16/32/64. */
+size_t seunet_conv_scratch_bytes(int Cin, int Cout, int ksize, int dil);
+int seunet_conv_fprop(const void* in, int in_chunks, int in_chunk_off, const float* w, int N, int D, int H, int W,
+                      int Cin, int Cout, int ksize, int dil, void* out, double* stats, void* scratch,
+                      int transpose_flip, seunet_stream_t stream);
+/* fp32 NCDHW <-> chunk-plane storage conversion helpers (tests, sliding-window driver). */
+int seunet_to_chunks(const float* src, int N, int C, int D, int H, int W, void* dst, int dst_chunks, int dst_off,
+                     seunet_stream_t stream);
+int seunet_from_chunks(const void* src, int src_chunks, int src_off, int N, int C, int D, int H, int W, float* dst,
+                       seunet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEUNET_B200_H */

@@ -1,0 +1,256 @@
+"""CPU/fp32 ORACLE for the SE_UNet hot path - TEST INFRASTRUCTURE ONLY.
+
+This module is a plain-PyTorch (fp32, functional) restatement of the reference algorithm
+(Beryl2000/SE-UNet-AirSeg).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs may import it, and only as the checker / CPU baseline - never as the
+product path.  The product (se_unet_airseg_b200) must not import anything from oracle/.
+
+Pinning: the reference ships no tests, golden vectors or weights for this path, so
+the oracle is pinned against outputs of the reference module itself, imported unmodified from
+/root/reference in the build container:
+  * tests/test_oracle_pin.py compares it live against /root/reference/SE_UNet.py when present;
+  * oracle/make_golden.py (committed) generated tests/golden/*.npz from the reference module;
+    tests/test_oracle_golden.py replays them anywhere (the GPU box has no /root/reference).
+
+Every function cites the reference file:line it follows.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# ---------------------------------------------------------------------------------------------
+# parameter schema (SE_UNet.py:108-153; registration order == state_dict order)
+# ---------------------------------------------------------------------------------------------
+# (name, kind, cin, cout, dilation, side-branch up-sample factor)
+SSE = "sse"    # SSEConv  (SE_UNet.py:9-35)   one sSE gate
+SSE2 = "sse2"  # SSEConv2 (SE_UNet.py:51-82)  two sSE gates
+CAT = "cat"    # CATConv  (SE_UNet.py:37-49)
+
+
+def layer_schema(in_channel=1):
+    ic = in_channel
+    return [
+        ("ec1", SSE, ic, 8, 1, 1), ("ec2", SSE, 8, 16, 1, 1), ("ec3", SSE, 16, 32, 2, 1),
+        ("ec33", CAT, 56, 32, 0, 0), ("x33", CAT, ic, 32, 0, 0),
+        ("ec4", SSE2, 32, 32, 1, 2), ("ec5", SSE2, 32, 32, 2, 2), ("ec6", SSE2, 32, 64, 2, 2),
+        ("ec63", CAT, 128, 64, 0, 0), ("x63", CAT, ic, 64, 0, 0),
+        ("ec7", SSE2, 64, 64, 1, 4), ("ec8", SSE2, 64, 64, 2, 4), ("ec9", SSE2, 64, 64, 2, 4),
+        ("ec93", CAT, 192, 64, 0, 0), ("x93", CAT, ic, 64, 0, 0),
+        ("ec10", SSE2, 64, 64, 1, 8), ("ec11", SSE2, 64, 64, 1, 8), ("ec12", SSE2, 64, 64, 1, 8),
+        ("ec123", CAT, 192, 64, 0, 0),
+        ("dc1", SSE2, 128, 64, 1, 4), ("dc2", SSE2, 64, 64, 1, 4), ("dc22", CAT, 128, 64, 0, 0),
+        ("dc3", SSE2, 128, 64, 1, 2), ("dc4", SSE2, 64, 32, 1, 2), ("dc42", CAT, 96, 32, 0, 0),
+        ("dc5", SSE, 64, 32, 1, 1), ("dc6", SSE, 32, 16, 1, 1), ("dc62", CAT, 48, 16, 0, 0),
+    ]
+
+
+def param_shapes(in_channel=1, n_classes=1):
+    """Ordered {name: shape} of the 117 state_dict tensors."""
+    out = {}
+    for name, kind, cin, cout, _dil, _up in layer_schema(in_channel):
+        if kind == CAT:
+            out[f"{name}.conv1.weight"] = (cout, cin, 1, 1, 1)
+            continue
+        out[f"{name}.conv1.weight"] = (cout, cin, 3, 3, 3)
+        out[f"{name}.conv1.bias"] = (cout,)
+        out[f"{name}.conv2.weight"] = (2, cout, 1, 1, 1)
+        out[f"{name}.conv2.bias"] = (2,)
+        out[f"{name}.conv_se.weight"] = (1, cout, 1, 1, 1)
+        if kind == SSE2:
+            out[f"{name}.conv_se2.weight"] = (1, cout, 1, 1, 1)
+    out["dc0_0.weight"] = (n_classes, 24, 1, 1, 1)
+    out["dc0_0.bias"] = (n_classes,)
+    out["dc0_1.weight"] = (n_classes, 12, 1, 1, 1)
+    out["dc0_1.bias"] = (n_classes,)
+    return out
+
+
+def init_params(in_channel=1, n_classes=1, seed=777, dtype=torch.float32):
+    """Deterministic parameters with nn.Conv3d's default init law (kaiming_uniform(a=sqrt(5)) ==
+    U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias), drawn from a private generator."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in param_shapes(in_channel, n_classes).items():
+        if name.endswith("weight"):
+            fan_in = shape[1] * shape[2] * shape[3] * shape[4]
+        else:
+            wshape = param_shapes(in_channel, n_classes)[name[:-4] + "weight"]
+            fan_in = wshape[1] * wshape[2] * wshape[3] * wshape[4]
+        bound = 1.0 / math.sqrt(fan_in)
+        sd[name] = ((torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+    return sd
+
+
+# ---------------------------------------------------------------------------------------------
+# blocks
+# ---------------------------------------------------------------------------------------------
+def _inorm(x):
+    # nn.InstanceNorm3d(C): eps 1e-5, affine=False, no running stats (SE_UNet.py:17,43,59)
+    return F.instance_norm(x, eps=1e-5)
+
+
+def _lrelu(x):
+    # nn.LeakyReLU(): negative_slope 0.01 (SE_UNet.py:18,44,60)
+    return F.leaky_relu(x, 0.01)
+
+
+def _up(x, factor):
+    # nn.Upsample(scale_factor, mode='trilinear', align_corners=True) (SE_UNet.py:19,61,136-138)
+    if factor == 1:
+        return x
+    return F.interpolate(x, scale_factor=factor, mode="trilinear", align_corners=True)
+
+
+def sse_block(sd, name, x, dil, up, gates):
+    """SSEConv.forward (SE_UNet.py:24-35) / SSEConv2.forward (SE_UNet.py:68-82)."""
+    e0 = F.conv3d(x, sd[f"{name}.conv1.weight"], sd[f"{name}.conv1.bias"], padding=dil, dilation=dil)
+    e0 = _lrelu(_inorm(e0))
+    e0 = e0 * torch.sigmoid(F.conv3d(e0, sd[f"{name}.conv_se.weight"]))
+    if gates == 2:
+        e0 = e0 * torch.sigmoid(F.conv3d(e0, sd[f"{name}.conv_se2.weight"]))
+    e1 = F.conv3d(e0, sd[f"{name}.conv2.weight"], sd[f"{name}.conv2.bias"])
+    return e0, _up(e1, up)
+
+
+def cat_block(sd, name, x):
+    """CATConv.forward (SE_UNet.py:45-49)."""
+    return _lrelu(_inorm(F.conv3d(x, sd[f"{name}.conv1.weight"])))
+
+
+def drop_scale(batch, channel_num, threshold=0.3, generator=None):
+    """DropLayer's per-(sample, channel) factor (SE_UNet.py:91-94): r = rand(B,C,1,1,1) on the CPU
+    generator, binarised at `threshold`, then r*C/(r.sum()+0.01) with the sum over the WHOLE batch."""
+    r = torch.rand(batch, channel_num, 1, 1, 1, generator=generator)
+    r = (r >= threshold).to(torch.float32)
+    return r * channel_num / (r.sum() + 0.01)
+
+
+def forward(sd, x, drop0=None, drop1=None):
+    """SE_UNet.forward (SE_UNet.py:181-238). drop0/drop1: DropLayer factors of shape (B,24,1,1,1) /
+    (B,12,1,1,1) in training mode, None in eval mode. Returns raw logits (pred0, pred1)."""
+    sch = {n: (k, dil, up) for n, k, _ci, _co, dil, up in layer_schema(x.shape[1])}
+
+    def sse(n, t):
+        k, dil, up = sch[n]
+        return sse_block(sd, n, t, dil, up, 2 if k == SSE2 else 1)
+
+    e0, s0 = sse("ec1", x)                                            # :183
+    e1, s1 = sse("ec2", e0)                                           # :184
+    e1_1, s2 = sse("ec3", e1)                                         # :185
+    e1 = cat_block(sd, "ec33", torch.cat((e1_1, e0, e1), 1))          # :186
+    e1 = e1 + cat_block(sd, "x33", x)                                 # :187
+    e2 = F.max_pool3d(e1, 2, 2)                                       # :188
+    x = F.max_pool3d(x, 2, 2)                                         # :189
+    e2, s3 = sse("ec4", e2)                                           # :192
+    e3, s4 = sse("ec5", e2)                                           # :193
+    e3_1, s5 = sse("ec6", e3)                                         # :194
+    e3 = cat_block(sd, "ec63", torch.cat((e3_1, e2, e3), 1))          # :195
+    e3 = e3 + cat_block(sd, "x63", x)                                 # :196
+    e4 = F.max_pool3d(e3, 2, 2)                                       # :197
+    x = F.max_pool3d(x, 2, 2)                                         # :198
+    e4, s6 = sse("ec7", e4)                                           # :201
+    e5, s7 = sse("ec8", e4)                                           # :202
+    e5_1, s8 = sse("ec9", e5)                                         # :203
+    e5 = cat_block(sd, "ec93", torch.cat((e5_1, e4, e5), 1))          # :204
+    e5 = e5 + cat_block(sd, "x93", x)                                 # :205
+    e6 = F.max_pool3d(e5, 2, 2)                                       # :206
+    e6, s9 = sse("ec10", e6)                                          # :209
+    e7, s10 = sse("ec11", e6)                                         # :210
+    e7_1, s11 = sse("ec12", e7)                                       # :211
+    e7 = cat_block(sd, "ec123", torch.cat((e7_1, e6, e7), 1))         # :212
+    e8 = _up(e7, 2)                                                   # :214
+    d0, s12 = sse("dc1", torch.cat((e8, e5), 1))                      # :216
+    d0_1, s13 = sse("dc2", d0)                                        # :217
+    d0 = cat_block(sd, "dc22", torch.cat((d0_1, d0), 1))              # :218
+    d1 = _up(d0, 2)                                                   # :220
+    d1, s14 = sse("dc3", torch.cat((d1, e3), 1))                      # :222
+    d1_1, s15 = sse("dc4", d1)                                        # :223
+    d1 = cat_block(sd, "dc42", torch.cat((d1_1, d1), 1))              # :224
+    d2 = _up(d1, 2)                                                   # :226
+    d2, s16 = sse("dc5", torch.cat((d2, e1), 1))                      # :228
+    _d2_1, s17 = sse("dc6", d2)                                       # :229
+    # :230 dc62(cat(d2_1, d2)) is computed by the reference but never used - omitted.
+    h0 = torch.cat((s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11), 1)
+    h1 = torch.cat((s12, s13, s14, s15, s16, s17), 1)
+    if drop0 is not None:
+        h0 = h0 * drop0                                               # :95
+    if drop1 is not None:
+        h1 = h1 * drop1
+    pred0 = F.conv3d(h0, sd["dc0_0.weight"], sd["dc0_0.bias"])        # :232
+    pred1 = F.conv3d(h1, sd["dc0_1.weight"], sd["dc0_1.bias"])        # :233
+    return pred0, pred1
+
+
+# ---------------------------------------------------------------------------------------------
+# losses (train.py; inputs are sigmoid probabilities, sums over the whole batch)
+# ---------------------------------------------------------------------------------------------
+def dice_loss(pred, target):
+    """train.py:51-57."""
+    smooth = 1.0
+    iflat = pred.reshape(-1)
+    tflat = target.reshape(-1)
+    intersection = (iflat * tflat).sum()
+    return 1.0 - ((2.0 * intersection + smooth) / (iflat.sum() + tflat.sum() + smooth))
+
+
+def general_union_loss_lib(pred, target, weight):
+    """train.py:59-68 (alpha 0.2, root exponent 0.7; sigma1 == sigma2 == 1e-4)."""
+    smooth = 1.0
+    alpha = 0.2
+    beta = 1 - alpha
+    sigma1 = 0.0001
+    sigma2 = 0.0001
+    weight_i = target * sigma1 + (1 - target) * sigma2
+    intersection = (weight * ((pred + weight_i) ** 0.7) * target).sum()
+    intersection2 = (weight * (alpha * pred + beta * target)).sum()
+    return 1 - (intersection + smooth) / (intersection2 + smooth)
+
+
+def atr_loss(pred, target, skel, weight):
+    """train.py:70-76 (the label argument is overwritten by the skeleton mask)."""
+    smooth = 1.0
+    target = skel
+    pred = pred * skel
+    intersection = (weight * pred * target).sum()
+    intersection2 = (weight * (pred + target)).sum()
+    return 1 - (intersection + smooth) / (intersection2 + smooth)
+
+
+def stage_loss(stage, pred_en, pred_de, label, weight=None, skel=None):
+    """Loss combinations of the three curriculum stages on raw logits:
+    stage 1 train.py:595-599, stage 2 train.py:429-435, stage 3 train.py:234-243."""
+    pe, pd = torch.sigmoid(pred_en), torch.sigmoid(pred_de)
+    if stage == 1:
+        return dice_loss(pd, label) + dice_loss(pe, label)
+    loss = general_union_loss_lib(pd, label, weight) + 0.5 * general_union_loss_lib(pe, label, weight)
+    if stage == 3:
+        loss = loss + 0.5 * (atr_loss(pe, label, skel, weight) + atr_loss(pd, label, skel, weight))
+    return loss
+
+
+# ---------------------------------------------------------------------------------------------
+# sliding-window helpers (prediction.py)
+# ---------------------------------------------------------------------------------------------
+def window_starts(length, cube=128, step=64):
+    """prediction.py:80-100 window enumeration along one axis: starts at k*step, the last window is
+    clamped to length-cube."""
+    if (length - cube) % step == 0:
+        n = (length - cube) // step + 1
+    else:
+        n = (length - cube) // step + 2
+    out = []
+    for i in range(n):
+        lo = i * step
+        if lo + cube > length:
+            lo = length - cube
+        out.append(lo)
+    return out
+
+
+def two_channel(img_hu):
+    """prediction.py:39-49 on HU values (after the -1024 shift of prediction.py:69): windows
+    [-1024, 1024] and [-1000, 500], clipped and scaled to [0, 1]."""
+    a = (img_hu.clamp(-1024.0, 1024.0) + 1024.0) / 2048.0
+    b = (img_hu.clamp(-1000.0, 500.0) + 1000.0) / 1500.0
+    return torch.stack((a, b), 0)

@@ -1,0 +1,61 @@
+"""Builds the C-ABI CUDA library (sm_100a only) in-tree with nvcc.
+
+The library is the product: if it is missing or stale the host module raises - there is no
+PyTorch/CPU fallback for the hot path.
+"""
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libseunet_b200.so")
+STAMP = os.path.join(HERE, ".libseunet_b200.stamp")
+SOURCES = ["conv_tc.cu", "pointwise.cu", "backward.cu", "plan.cu"]  # missing files are skipped
+HEADERS = ["common.cuh", "conv_tc.cuh", "pointwise.cuh", "backward.cuh", os.path.join("..", "..", "include", "seunet_b200.h")]
+
+NVCC_FLAGS = [
+    "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+]
+
+
+def _source_hash(extra):
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS:
+        p = os.path.join(CSRC, f)
+        if os.path.exists(p):
+            with open(p, "rb") as fh:
+                h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + extra).encode())
+    return h.hexdigest()
+
+
+def build(force=False, bf16=None, verbose=False):
+    """Compile libseunet_b200.so if sources changed. Returns the library path."""
+    if bf16 is None:
+        bf16 = os.environ.get("SEUNET_ACT_BF16", "0") == "1"
+    extra = ["-DSEUNET_ACT_BF16"] if bf16 else []
+    want = _source_hash(extra)
+    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
+        with open(STAMP) as fh:
+            if fh.read().strip() == want:
+                return LIB
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + srcs + ["-o", LIB]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr, file=sys.stderr)
+    with open(STAMP, "w") as fh:
+        fh.write(want)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,503 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a.
+//
+// Replaces the reference's nn.Conv3d call sites SE_UNet.py:15/57 (3x3x3, dilation 1|2, padding=dilation)
+// and SE_UNet.py:42 (CATConv 1x1x1), forward (and data-gradient, with mirrored/transposed weights).
+//
+// GEMM view:  out[voxel, cout] = sum_{tap, cin} in[voxel + shift(tap), cin] * W[tap, cin, cout].
+//   * UMMA M = 128 voxels  = a 16(h) x 8(w) patch of ONE d-plane.
+//   * UMMA K = 16 channels of one (kh,kw) tap.  Activations live in HBM as [n][C/8][D][H][W][8]
+//     ("chunk planes"), and one TMA box brings a halo'd (16+2h)x(8+2h) patch of KC channels of one
+//     input plane into shared memory as [KC/8][hh][ww][8].  In the no-swizzle K-major canonical UMMA
+//     layout ((8,m),2):((16B,SBO),LBO) this means: the 8 rows of a core matrix are 8 consecutive w
+//     voxels, SBO = one halo line, LBO = one chunk plane - and EVERY (kh,kw) tap is just a different
+//     start address into the same halo tile.  Activations are therefore read from L2 once per
+//     input plane (x1.4-1.9 halo) instead of 27 times.
+//   * UMMA N = 3*Cout: the three kd taps that consume the same input plane q are stacked along N.
+//     They accumulate into the output planes q-dil, q, q+dil, whose TMEM accumulators are laid out
+//     adjacently (for dil=2 the even planes first, then the odd ones), so one instruction with
+//     N = 3*Cout feeds three accumulators.  This triples the reuse of the A tile read from shared
+//     memory, which is what limits small-N UMMA shapes.
+//   * A CTA tile is DT = 256/Cout output planes of one 16x8 patch; two TMEM accumulator stages
+//     (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//   * Weights are pre-packed into the exact shared-memory image ([chunk][step][khalf][3*Cout][8]) and
+//     either stay resident for the whole (persistent) CTA or stream through a 2-slot ring when
+//     27*Cin*Cout*2 B does not fit (Cin*Cout >= 64*64).
+//   * Epilogue: TMEM -> registers -> fp16/bf16 raw conv output (chunk planes) + per-(n,c) sum / sum
+//     of squares for InstanceNorm (fp32 partials from the fp32 accumulators, fp64 atomics).
+#include "conv_tc.cuh"
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+// ---------------------------------------------------------------------------------------------
+// device
+// ---------------------------------------------------------------------------------------------
+struct TileCoord { int n, d0, h0, w0; };
+
+template <int DT>
+__device__ __forceinline__ TileCoord decode_tile(const ConvKArgs& a, int tile) {
+  TileCoord t;
+  const int tw = tile % a.tilesW; tile /= a.tilesW;
+  const int th = tile % a.tilesH; tile /= a.tilesH;
+  const int td = tile % a.tilesD; tile /= a.tilesD;
+  t.n = tile; t.d0 = td * DT; t.h0 = th * kConvTileH; t.w0 = tw * kConvTileW;
+  return t;
+}
+
+// accumulator slot of output plane p_rel (tile-relative): planes that share one input plane must be
+// adjacent, i.e. for dilation 2 the even planes come first, then the odd ones.
+template <int DT>
+__device__ __forceinline__ int plane_slot(int p_rel, int dil) {
+  return dil == 2 ? ((p_rel & 1) * (DT / 2) + (p_rel >> 1)) : p_rel;
+}
+template <int DT>
+__device__ __forceinline__ int slot_plane(int slot, int dil) {
+  return dil == 2 ? ((slot % (DT / 2)) * 2 + slot / (DT / 2)) : slot;
+}
+
+// Range [jlo, jhi] of stacked kd blocks (j=0 -> kd=2 -> output plane q-dil, j=1 -> q, j=2 -> q+dil)
+// that are valid for tile-relative input plane q_rel.  Returns false when the plane is not needed.
+template <int DT>
+__device__ __forceinline__ bool plane_jrange(const ConvKArgs& a, int d0, int q_rel, int& jlo, int& jhi) {
+  const int q = d0 + q_rel;
+  jlo = 3; jhi = -1;
+  if (q < 0 || q >= a.D) return false;
+  if (a.nkd == 1) {
+    jlo = jhi = 0;
+    return q_rel >= 0 && q_rel < DT;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int p = q_rel + (j - 1) * a.dil;
+    if (p >= 0 && p < DT && d0 + p < a.D) { jlo = min(jlo, j); jhi = max(jhi, j); }
+  }
+  return jhi >= 0;
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvKArgs a) {
+  constexpr int DT = kConvAccCols / COUT;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  // dynamic smem base is only guaranteed 16-byte aligned: align to 128 by hand
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t w_region = (a.wslots * a.wchunk_bytes + 127u) & ~127u;
+  const uint32_t w_addr = smem_base;
+  const uint32_t s_addr = smem_base + w_region;
+  const uint32_t bar_addr = s_addr + a.nstages * a.stage_bytes;
+  // barrier slots (8 bytes each)
+  auto full_bar = [&](int i) { return bar_addr + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_addr + 8u * (16 + i); };
+  auto wfull_bar = [&](int i) { return bar_addr + 8u * (32 + i); };
+  auto wempty_bar = [&](int i) { return bar_addr + 8u * (40 + i); };
+  auto tfull_bar = [&](int i) { return bar_addr + 8u * (48 + i); };
+  auto tempty_bar = [&](int i) { return bar_addr + 8u * (50 + i); };
+  const uint32_t tmem_slot_addr = bar_addr + 8u * 52;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.nstages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+    for (int i = 0; i < a.wslots; ++i) { mbar_init(wfull_bar(i), 1); mbar_init(wempty_bar(i), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot_addr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot_addr));
+
+  const bool resident = a.nchunks <= a.wslots;
+  const int nq = DT + 2 * a.dil;  // candidate input planes per tile (dil == 0 for pointwise)
+
+  if (warp == 0) {
+    // =================================== TMA producer ===================================
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0, wcount = 0;
+      auto load_weights = [&](int chunk, int slot) {
+        mbar_expect_tx(wfull_bar(slot), a.wchunk_bytes);
+        const uint8_t* src = a.wimg + (size_t)chunk * a.wchunk_bytes;
+        const uint32_t dst = w_addr + slot * a.wchunk_bytes;
+        for (uint32_t off = 0; off < a.wchunk_bytes; off += 16384u) {
+          const uint32_t n = min(16384u, a.wchunk_bytes - off);
+          bulk_g2s(dst + off, src + off, n, wfull_bar(slot));
+        }
+      };
+      if (resident)
+        for (int c = 0; c < a.nchunks; ++c) load_weights(c, c);
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile<DT>(a, tile);
+        for (int c = 0; c < a.nchunks; ++c) {
+          if (!resident) {
+            const int slot = wcount % a.wslots;
+            const uint32_t par = (wcount / a.wslots) & 1u;
+            mbar_wait(wempty_bar(slot), par ^ 1u);
+            load_weights(c, slot);
+            ++wcount;
+          }
+          for (int qi = 0; qi < nq; ++qi) {
+            int jlo, jhi;
+            const int q_rel = qi - a.dil;
+            if (!plane_jrange<DT>(a, t.d0, q_rel, jlo, jhi)) continue;
+            mbar_wait(empty_bar(st), ph ^ 1u);
+            mbar_expect_tx(full_bar(st), a.box_bytes);
+            tma_load_4d(s_addr + st * a.stage_bytes, &tmap, full_bar(st),
+                        8 * (t.w0 - a.halo), t.h0 - a.halo, t.d0 + q_rel,
+                        t.n * a.in_chunks_total + a.in_chunk_off + c * a.kc8);
+            if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =================================== UMMA issuer ===================================
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0, wcount = 0, acc = 0, accph = 0, wready = 0;
+      const uint32_t idesc1 = umma_idesc(SEUNET_UMMA_FMT, 128, COUT);
+      const uint32_t idesc2 = umma_idesc(SEUNET_UMMA_FMT, 128, 2 * COUT);
+      const uint32_t idesc3 = umma_idesc(SEUNET_UMMA_FMT, 128, 3 * COUT);
+      for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile<DT>(a, tile);
+        mbar_wait(tempty_bar(acc), accph ^ 1u);
+        tc_fence_after();
+        uint32_t touched = 0;
+        for (int c = 0; c < a.nchunks; ++c) {
+          int slot;
+          if (resident) {
+            slot = c;
+            if (!((wready >> c) & 1u)) { mbar_wait(wfull_bar(c), 0); wready |= 1u << c; }
+          } else {
+            slot = wcount % a.wslots;
+            mbar_wait(wfull_bar(slot), (wcount / a.wslots) & 1u);
+          }
+          const uint32_t wsm = w_addr + slot * a.wchunk_bytes;
+          for (int qi = 0; qi < nq; ++qi) {
+            int jlo, jhi;
+            const int q_rel = qi - a.dil;
+            if (!plane_jrange<DT>(a, t.d0, q_rel, jlo, jhi)) continue;
+            const int nj = jhi - jlo + 1;
+            const int p_lo = (a.nkd == 1) ? q_rel : q_rel + (jlo - 1) * a.dil;
+            const int slot_lo = plane_slot<DT>(p_lo, a.dil);
+            const uint32_t dcol = tmem_base + acc * kConvAccCols + slot_lo * COUT;
+            const uint32_t idesc = nj == 3 ? idesc3 : (nj == 2 ? idesc2 : idesc1);
+            mbar_wait(full_bar(st), ph);
+            tc_fence_after();
+            const uint32_t a_addr = s_addr + st * a.stage_bytes;
+            const uint32_t b_addr = wsm + jlo * COUT * 16;
+            for (int s = 0; s < a.nsteps; ++s) {
+              const ConvStep stp = a.steps[s];
+              const uint64_t adesc = umma_desc(a_addr + stp.a_off, stp.a_lbo, a.a_sbo);
+              if (c == 0 && s == 0) {
+                // first contribution of this input plane: the stacked accumulators may differ in
+                // whether they were written before, so issue one N=COUT instruction per plane.
+                for (int jj = 0; jj < nj; ++jj) {
+                  const int sl = slot_lo + jj;
+                  const uint64_t bdesc = umma_desc(b_addr + stp.b_off + jj * COUT * 16, a.b_lbo, 128);
+                  umma_f16(dcol + jj * COUT, adesc, bdesc, idesc1, (touched >> sl) & 1u);
+                  touched |= 1u << sl;
+                }
+              } else {
+                const uint64_t bdesc = umma_desc(b_addr + stp.b_off, a.b_lbo, 128);
+                umma_f16(dcol, adesc, bdesc, idesc, 1u);
+              }
+            }
+            umma_commit(empty_bar(st));  // frees the activation stage when these MMAs retire
+            if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
+          }
+          if (!resident) { umma_commit(wempty_bar(slot)); ++wcount; }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1u;
+        if (acc == 0) accph ^= 1u;
+      }
+    }
+  } else {
+    // =================================== epilogue (4 warps) ===================================
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
+    const int row = quarter * 32 + lane;
+    const int hh = row >> 3, ww = row & 7;
+    uint32_t acc = 0, accph = 0;
+    for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile<DT>(a, tile);
+      const int h = t.h0 + hh, w = t.w0 + ww;
+      const bool inb = (h < a.H) && (w < a.W);
+      mbar_wait(tfull_bar(acc), accph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kConvAccCols;
+      const size_t plane_elems = (size_t)a.H * a.W * 8;
+#pragma unroll 1
+      for (int cg = 0; cg < COUT / 16; ++cg) {
+        float red[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) red[i] = 0.f;
+        act_t* obase = a.out +
+            ((size_t)(t.n * a.out_chunks_total + a.out_chunk_off + cg * 2) * a.D) * plane_elems +
+            ((size_t)h * a.W + w) * 8;
+#pragma unroll 1
+        for (int s = 0; s < DT; ++s) {
+          const int d = t.d0 + slot_plane<DT>(s, a.dil);
+          if (d >= a.D) continue;  // warp-uniform
+          uint32_t v[16];
+          tmem_ld16(tacc + s * COUT + cg * 16, v);
+          tmem_ld_wait();
+          if (inb) {
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              f[i] = __uint_as_float(v[i]);
+              red[i] += f[i];
+              red[16 + i] += f[i] * f[i];
+            }
+            act_t* o = obase + (size_t)d * plane_elems;
+            st_chunk(o, floats_to_chunk(f));
+            st_chunk(o + (size_t)a.D * plane_elems, floats_to_chunk(f + 8));
+          }
+        }
+        const float tot = warp_xreduce32(red, lane);
+        // lane l < 16: sum of channel cg*16+l ; lane l >= 16: sum of squares of channel cg*16+l-16
+        double* sp = a.stats + ((size_t)t.n * COUT + cg * 16 + (lane & 15)) * 2 + (lane >> 4);
+        atomicAdd(sp, (double)tot);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1u;
+      if (acc == 0) accph ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: fp32 (Cout, Cin, k,k,k) -> UMMA image [chunk][step][khalf][nkd*COUT][8]
+// ---------------------------------------------------------------------------------------------
+struct PackArgs {
+  int Cin_real, Cout_real, COUT, ksize, nkd, KC, nchunks, nsteps, transpose_flip;
+  PackStep steps[kConvMaxSteps];
+};
+
+__global__ void conv_pack_kernel(const float* __restrict__ w, act_t* __restrict__ img, const __grid_constant__ PackArgs p) {
+  const int rows = p.nkd * p.COUT;
+  const size_t total = (size_t)p.nchunks * p.nsteps * 2 * rows * 8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int e = r % 8; r /= 8;
+    const int row = r % rows; r /= rows;
+    const int khalf = r % 2; r /= 2;
+    const int s = r % p.nsteps; r /= p.nsteps;
+    const int c = (int)r;
+    const PackStep ps = p.steps[s];
+    const int tap = khalf ? ps.tap_b : ps.tap_a;
+    const int ci = c * p.KC + (khalf ? ps.cbase_b : ps.cbase_a) + e;
+    const int jkd = row / p.COUT, co = row % p.COUT;
+    float val = 0.f;
+    if (tap >= 0) {
+      int kd = (p.nkd == 3) ? (2 - jkd) : 0;
+      int kh = tap / 3, kw = tap % 3;
+      const int K = p.ksize, K3 = K * K * K;
+      if (!p.transpose_flip) {
+        if (co < p.Cout_real && ci < p.Cin_real)
+          val = w[((size_t)co * p.Cin_real + ci) * K3 + (kd * K + kh) * K + kw];
+      } else {
+        // data gradient: "input" channels are the forward Cout, "output" channels the forward Cin,
+        // taps mirrored.  Cin_real/Cout_real are given in the gradient operator's own roles.
+        if (co < p.Cout_real && ci < p.Cin_real) {
+          if (K == 3) { kd = 2 - kd; kh = 2 - kh; kw = 2 - kw; }
+          val = w[((size_t)ci * p.Cout_real + co) * K3 + (kd * K + kh) * K + kw];
+        }
+      }
+    }
+    img[i] = f2act(val);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+static constexpr uint32_t kSmemBudget = 225u * 1024u;
+static constexpr uint32_t kBarBytes = 8u * 64u;
+
+int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil) {
+  memset(g, 0, sizeof(*g));
+  g->Cin_real = Cin_real; g->Cout_real = Cout_real; g->ksize = ksize; g->dil = (ksize == 3) ? dil : 0;
+  if (ksize != 1 && ksize != 3) { seunet_set_error("conv: kernel size %d unsupported", ksize); return 1; }
+  if (ksize == 3 && dil != 1 && dil != 2) { seunet_set_error("conv: dilation %d unsupported", dil); return 1; }
+  g->COUT = Cout_real <= 16 ? 16 : (Cout_real <= 32 ? 32 : 64);
+  if (Cout_real > 64) { seunet_set_error("conv: Cout %d > 64 unsupported", Cout_real); return 1; }
+  const int nkd = ksize == 3 ? 3 : 1;
+  const int ntaps = ksize == 3 ? 9 : 1;
+  const int halo = g->dil;
+  const int HV = (kConvTileH + 2 * halo) * (kConvTileW + 2 * halo);
+  int Cin = Cin_real <= 8 ? 8 : ((Cin_real + 15) / 16) * 16;
+  if (ksize == 1 && Cin == 8) Cin = 16;
+  g->Cin = Cin;
+  g->paired = (Cin == 8);
+  if (g->paired) {
+    g->KC = 8; g->nchunks = 1; g->nsteps = 5;
+    for (int s = 0; s < 5; ++s) {
+      g->psteps[s].tap_a = (int8_t)(2 * s);
+      g->psteps[s].tap_b = (int8_t)(2 * s + 1 < 9 ? 2 * s + 1 : -1);
+      g->psteps[s].cbase_a = 0; g->psteps[s].cbase_b = 0;
+    }
+  } else {
+    const size_t total_w = (size_t)Cin * ntaps * nkd * g->COUT * 2;
+    int KC;
+    if (total_w <= 112u * 1024u) {
+      KC = 64;
+      while (Cin % KC) KC /= 2;
+      g->wslots = Cin / KC;
+    } else {
+      KC = 16;
+      g->wslots = 2;
+    }
+    g->KC = KC; g->nchunks = Cin / KC;
+    g->nsteps = ntaps * (KC / 16);
+    for (int t = 0; t < ntaps; ++t)
+      for (int j = 0; j < KC / 16; ++j) {
+        PackStep& ps = g->psteps[t * (KC / 16) + j];
+        ps.tap_a = ps.tap_b = (int8_t)t;
+        ps.cbase_a = (int16_t)(j * 16); ps.cbase_b = (int16_t)(j * 16 + 8);
+      }
+  }
+  if (g->paired) g->wslots = 1;
+  if (g->nsteps > kConvMaxSteps) { seunet_set_error("conv: too many steps"); return 1; }
+  g->wchunk_bytes = (uint32_t)g->nsteps * 2u * nkd * g->COUT * 16u;
+  g->box_bytes = (uint32_t)HV * g->KC * 2u;
+  g->stage_bytes = (g->box_bytes + 127u) & ~127u;
+  const uint32_t wregion = ((uint32_t)g->wslots * g->wchunk_bytes + 127u) & ~127u;
+  int nst = (int)((kSmemBudget - wregion - kBarBytes - 128u) / g->stage_bytes);
+  nst = std::min(nst, 12);
+  if (nst < 2) { seunet_set_error("conv: shared memory budget exceeded"); return 1; }
+  g->nstages = nst;
+  g->smem_bytes = wregion + nst * g->stage_bytes + kBarBytes + 128u;
+  return 0;
+}
+
+int conv_pack_weights(const ConvGeom& g, const float* w_fp32, void* wimg, int transpose_flip, cudaStream_t st) {
+  PackArgs p;
+  memset(&p, 0, sizeof(p));
+  p.Cin_real = g.Cin_real; p.Cout_real = g.Cout_real; p.COUT = g.COUT; p.ksize = g.ksize;
+  p.nkd = g.ksize == 3 ? 3 : 1; p.KC = g.KC; p.nchunks = g.nchunks; p.nsteps = g.nsteps;
+  p.transpose_flip = transpose_flip;
+  memcpy(p.steps, g.psteps, sizeof(p.steps));
+  const size_t total = g.wimg_bytes() / 2;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 1024);
+  conv_pack_kernel<<<blocks, 256, 0, st>>>(w_fp32, (act_t*)wimg, p);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (PFN_encodeTiled)p;
+  return fn;
+}
+
+int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int W,
+                     const void* in, int in_chunks_total, int in_chunk_off,
+                     void* out, int out_chunks_total, int out_chunk_off,
+                     double* stats, const void* wimg, int num_sms) {
+  L->g = g;
+  ConvKArgs& a = L->a;
+  memset(&a, 0, sizeof(a));
+  const int nkd = g.ksize == 3 ? 3 : 1;
+  const int halo = g.dil;
+  const int DT = kConvAccCols / g.COUT;
+  const int lineW = kConvTileW + 2 * halo;
+  const int HV = (kConvTileH + 2 * halo) * lineW;
+  a.N = N; a.D = D; a.H = H; a.W = W;
+  a.tilesW = (W + kConvTileW - 1) / kConvTileW;
+  a.tilesH = (H + kConvTileH - 1) / kConvTileH;
+  a.tilesD = (D + DT - 1) / DT;
+  a.numTiles = a.tilesW * a.tilesH * a.tilesD * N;
+  a.dil = nkd == 3 ? g.dil : 0;
+  a.nkd = nkd; a.halo = halo;
+  a.nchunks = g.nchunks; a.kc8 = g.KC / 8;
+  a.in_chunks_total = in_chunks_total; a.in_chunk_off = in_chunk_off;
+  a.out_chunks_total = out_chunks_total; a.out_chunk_off = out_chunk_off;
+  a.nstages = g.nstages; a.wslots = g.wslots; a.nsteps = g.nsteps;
+  a.stage_bytes = g.stage_bytes; a.box_bytes = g.box_bytes; a.wchunk_bytes = g.wchunk_bytes;
+  a.a_sbo = (uint32_t)lineW * 16u;
+  a.b_lbo = (uint32_t)nkd * g.COUT * 16u;
+  a.wimg = (const uint8_t*)wimg;
+  a.out = (act_t*)out;
+  a.stats = stats;
+  const uint32_t a_lbo = (uint32_t)HV * 16u;
+  for (int s = 0; s < g.nsteps; ++s) {
+    const PackStep& ps = g.psteps[s];
+    auto tapoff = [&](int t) { return (uint32_t)(((t / 3) * g.dil * lineW + (t % 3) * g.dil) * 16); };
+    ConvStep& cs = a.steps[s];
+    if (g.paired) {
+      cs.a_off = tapoff(ps.tap_a);
+      cs.a_lbo = ps.tap_b >= 0 ? tapoff(ps.tap_b) - tapoff(ps.tap_a) : 16u;
+    } else {
+      cs.a_off = (g.ksize == 3 ? tapoff(ps.tap_a) : 0u) + (uint32_t)(ps.cbase_a / 8) * a_lbo;
+      cs.a_lbo = a_lbo;
+    }
+    cs.b_off = (uint32_t)s * 2u * nkd * g.COUT * 16u;
+  }
+  if (in_chunk_off + g.Cin / 8 > in_chunks_total) { seunet_set_error("conv: input slice exceeds buffer"); return 1; }
+  if (out_chunk_off + g.COUT / 8 > out_chunks_total) { seunet_set_error("conv: output slice exceeds buffer"); return 1; }
+
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { seunet_set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)"); return 1; }
+  cuuint64_t gdim[4] = {(cuuint64_t)8 * W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N * in_chunks_total};
+  cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+  cuuint32_t box[4] = {(cuuint32_t)(8 * lineW), (cuuint32_t)(kConvTileH + 2 * halo), 1u, (cuuint32_t)(g.KC / 8)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+#ifdef SEUNET_ACT_BF16
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#else
+  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#endif
+  CUresult r = enc(&L->tmap, dt, 4, const_cast<void*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { seunet_set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return 1; }
+  L->grid = std::min(a.numTiles, num_sms);
+  return 0;
+}
+
+template <int COUT>
+static int conv_launch_t(const ConvLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SEUNET_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_tc_kernel<COUT><<<L.grid, kConvThreads, L.g.smem_bytes, st>>>(L.tmap, L.a);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int conv_launch_run(const ConvLaunch& L, cudaStream_t st) {
+  switch (L.g.COUT) {
+    case 16: return conv_launch_t<16>(L, st);
+    case 32: return conv_launch_t<32>(L, st);
+    case 64: return conv_launch_t<64>(L, st);
+  }
+  seunet_set_error("conv: bad COUT %d", L.g.COUT);
+  return 1;
+}

@@ -1,0 +1,76 @@
+// Host-side description of one tcgen05 implicit-GEMM convolution launch (3x3x3 dilated or 1x1x1).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+constexpr int kConvThreads = 192;   // warp 0: TMA producer, warp 1: UMMA issuer, warps 2-5: epilogue
+constexpr int kConvMaxSteps = 40;   // UMMA K=16 steps per (input plane, channel chunk)
+constexpr int kConvTileH = 16;      // one UMMA M=128 block = 16 (h) x 8 (w) voxels of one d-plane
+constexpr int kConvTileW = 8;
+constexpr int kConvAccCols = 256;   // TMEM columns per accumulator stage (2 stages = 512)
+
+struct ConvStep {
+  uint32_t a_off;   // byte offset of the A (activation) start address inside a stage
+  uint32_t a_lbo;   // byte distance between the two 8-channel K halves of this step
+  uint32_t b_off;   // byte offset of the step's weight block inside a weight chunk
+  uint32_t pad;
+};
+
+// Kernel arguments (passed by value as a __grid_constant__).
+struct ConvKArgs {
+  int N, D, H, W;
+  int tilesW, tilesH, tilesD, numTiles;
+  int dil;            // plane distance of the kd taps (0 when nkd == 1)
+  int nkd;            // 3: kd taps stacked along UMMA N; 1: pointwise conv
+  int halo;           // in-plane halo (dil for 3x3x3, 0 for 1x1x1)
+  int nchunks, kc8;   // channel chunks per tile, 8-channel planes per chunk
+  int in_chunks_total, in_chunk_off;
+  int out_chunks_total, out_chunk_off;
+  int nstages, wslots, nsteps;
+  uint32_t stage_bytes, box_bytes, wchunk_bytes;
+  uint32_t a_sbo, b_lbo;
+  const uint8_t* wimg;   // packed weights: [chunk][step][khalf][nkd*COUT rows][8]
+  act_t* out;            // raw conv output, chunk-plane layout
+  double* stats;         // [N][COUT][2] running (sum, sum of squares), fp64 atomics
+  ConvStep steps[kConvMaxSteps];
+};
+
+// How the fp32 reference weights map into one UMMA K=16 step of the packed image.
+struct PackStep {
+  int8_t tap_a, tap_b;      // (kh*3+kw) of K half 0 / 1, -1 = zeros
+  int16_t cbase_a, cbase_b; // channel offset inside the chunk of K half 0 / 1
+};
+
+struct ConvGeom {
+  int Cin_real, Cout_real;  // reference tensor sizes
+  int Cin, COUT;            // padded: Cin in {8, 16k}, COUT in {16,32,64}
+  int ksize;                // 3 or 1
+  int dil;                  // conv dilation (3x3x3 only)
+  int KC, nchunks, nsteps, wslots, nstages;
+  bool paired;              // Cin == 8: two taps share one K=16 step
+  uint32_t stage_bytes, box_bytes, wchunk_bytes, smem_bytes;
+  PackStep psteps[kConvMaxSteps];
+  size_t wimg_bytes() const { return (size_t)nchunks * wchunk_bytes; }
+};
+
+// Fill geometry for a layer. Returns 0 on success.
+int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil);
+
+// Pack fp32 weights (Cout_real, Cin_real, k, k, k) into the UMMA image.  transpose_flip=1 builds
+// the data-gradient operator (roles of Cin/Cout swapped, taps mirrored).
+int conv_pack_weights(const ConvGeom& g, const float* w_fp32, void* wimg, int transpose_flip, cudaStream_t st);
+
+struct ConvLaunch {
+  ConvGeom g;
+  CUtensorMap tmap;
+  ConvKArgs a;
+  int grid;
+};
+
+// Bind a layer to concrete buffers: input chunk-plane buffer (in_chunks_total planes per sample,
+// slice starting at in_chunk_off), output raw buffer, stats.
+int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int W,
+                     const void* in, int in_chunks_total, int in_chunk_off,
+                     void* out, int out_chunks_total, int out_chunk_off,
+                     double* stats, const void* wimg, int num_sms);
+int conv_launch_run(const ConvLaunch& L, cudaStream_t st);

@@ -1,0 +1,400 @@
+// HBM-bound forward kernels: input prep, fused InstanceNorm+LeakyReLU+sSE gate(s)+side-branch fold,
+// CAT-block apply (+ detail injection + 2x2x2 max-pool), trilinear x2 upsample, deep-supervision head.
+// All activations are chunk planes [n][C/8][D][H][W][8] so every thread moves 16-byte vectors and a
+// warp touches 512 contiguous bytes per chunk plane.
+#include "pointwise.cuh"
+#include <cstring>
+
+constexpr float kInEps = 1e-5f;   // nn.InstanceNorm3d default eps (SE_UNet.py:17,43,59)
+
+// =============================================================================================
+// input prep
+// =============================================================================================
+// One thread per 4x4x4 block of the full-resolution input: writes the 64 chunk-plane voxels, the
+// 8 half-resolution and 1 quarter-resolution max-pooled values (SE_UNet.py:189,198) and contributes
+// to the first/second moments of x at each level (used for the analytic InstanceNorm statistics of
+// the x33/x63/x93 injection branches).
+__global__ void __launch_bounds__(128) input_prep_kernel(const float* __restrict__ x, long long sN, long long sC, long long sD,
+                                                         long long sH, long long sW, int in_ch, Dims d,
+                                                         act_t* __restrict__ xb, float* __restrict__ xp1,
+                                                         float* __restrict__ xp2, double* __restrict__ mom) {
+  const int n = blockIdx.y;
+  const int D4 = d.D >> 2, H4 = d.H >> 2, W4 = d.W >> 2;
+  const long long nb = (long long)D4 * H4 * W4;
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  // moments: [level][5] = s0, s1, s00, s11, s01
+  float m[3][5];
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+#pragma unroll
+    for (int i = 0; i < 5; ++i) m[l][i] = 0.f;
+  if (b < nb) {
+    const int bw = (int)(b % W4), bh = (int)((b / W4) % H4), bd = (int)(b / ((long long)W4 * H4));
+    float p2[kMaxInCh];
+#pragma unroll
+    for (int c = 0; c < kMaxInCh; ++c) p2[c] = -INFINITY;
+    for (int dd2 = 0; dd2 < 2; ++dd2)
+      for (int hh2 = 0; hh2 < 2; ++hh2)
+        for (int ww2 = 0; ww2 < 2; ++ww2) {
+          float p1[kMaxInCh];
+#pragma unroll
+          for (int c = 0; c < kMaxInCh; ++c) p1[c] = -INFINITY;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int dz = bd * 4 + dd2 * 2 + (k >> 2), hy = bh * 4 + hh2 * 2 + ((k >> 1) & 1), wx = bw * 4 + ww2 * 2 + (k & 1);
+            float v[kMaxInCh];
+#pragma unroll
+            for (int c = 0; c < kMaxInCh; ++c)
+              v[c] = c < in_ch ? x[n * sN + c * sC + dz * sD + hy * sH + wx * sW] : 0.f;
+            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < kMaxInCh; ++c) { f[c] = v[c]; p1[c] = fmaxf(p1[c], v[c]); }
+            st_chunk(xb + (((size_t)n * d.D + dz) * d.H + hy) * (size_t)d.W * 8 + (size_t)wx * 8, floats_to_chunk(f));
+            m[0][0] += v[0]; m[0][1] += v[1]; m[0][2] += v[0] * v[0]; m[0][3] += v[1] * v[1]; m[0][4] += v[0] * v[1];
+          }
+          const int d1 = bd * 2 + dd2, h1 = bh * 2 + hh2, w1 = bw * 2 + ww2;
+#pragma unroll
+          for (int c = 0; c < kMaxInCh; ++c) {
+            if (c < in_ch) xp1[(((size_t)n * in_ch + c) * (d.D >> 1) + d1) * (size_t)(d.H >> 1) * (d.W >> 1) + (size_t)h1 * (d.W >> 1) + w1] = p1[c];
+            else p1[c] = 0.f;
+            p2[c] = fmaxf(p2[c], p1[c]);
+          }
+          m[1][0] += p1[0]; m[1][1] += p1[1]; m[1][2] += p1[0] * p1[0]; m[1][3] += p1[1] * p1[1]; m[1][4] += p1[0] * p1[1];
+        }
+#pragma unroll
+    for (int c = 0; c < kMaxInCh; ++c) {
+      if (c < in_ch) xp2[(((size_t)n * in_ch + c) * D4 + bd) * (size_t)H4 * W4 + (size_t)bh * W4 + bw] = p2[c];
+      else p2[c] = 0.f;
+    }
+    m[2][0] = p2[0]; m[2][1] = p2[1]; m[2][2] = p2[0] * p2[0]; m[2][3] = p2[1] * p2[1]; m[2][4] = p2[0] * p2[1];
+  }
+  // block reduce (fp32 per thread covers <= 64 values; cross-thread accumulation in fp64)
+  __shared__ double red[4][15];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const double s = warp_sum_d((double)m[l][i]);
+      if (lane == 0) red[warp][l * 5 + i] = s;
+    }
+  __syncthreads();
+  if (threadIdx.x < 15) {
+    const double s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    const int l = threadIdx.x / 5, i = threadIdx.x % 5;
+    atomicAdd(mom + ((size_t)l * gridDim.y + n) * kMomStride + i, s);
+  }
+}
+
+int launch_input_prep(const float* x, const long long* xs, int in_ch, Dims d, act_t* xb, float* xp1, float* xp2,
+                      double* mom, cudaStream_t st) {
+  if (in_ch < 1 || in_ch > kMaxInCh) { seunet_set_error("in_channel %d unsupported (1..%d)", in_ch, kMaxInCh); return 1; }
+  if ((d.D | d.H | d.W) & 7) { seunet_set_error("spatial dims must be multiples of 8"); return 1; }
+  SEUNET_CUDA_CHECK(cudaMemsetAsync(mom, 0, sizeof(double) * 3 * d.N * kMomStride, st));
+  const long long nb = (long long)(d.D / 4) * (d.H / 4) * (d.W / 4);
+  dim3 grid((unsigned)((nb + 127) / 128), d.N);
+  input_prep_kernel<<<grid, 128, 0, st>>>(x, xs[0], xs[1], xs[2], xs[3], xs[4], in_ch, d, xb, xp1, xp2, mom);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// SSE block apply:  y -> IN -> LeakyReLU -> sSE gate(s) -> e0 (+ folded conv2/head contribution)
+// (SE_UNet.py:26-33 / 70-80; fold of conv2 + up_sample + dc0_x per SURVEY App. C)
+// =============================================================================================
+template <int C, int GATES>
+__global__ void __launch_bounds__(256) apply_sse_kernel(const __grid_constant__ SseArgs a) {
+  __shared__ float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double s = a.stats[((size_t)n * a.stats_c + c) * 2], q = a.stats[((size_t)n * a.stats_c + c) * 2 + 1];
+    const double mean = s / (double)a.V;
+    double var = q / (double)a.V - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[c] = (float)mean;
+    s_rstd[c] = (float)(1.0 / sqrt(var + (double)kInEps));
+    s_wse[c] = a.wse[c];
+    s_wse2[c] = GATES == 2 ? a.wse2[c] : 0.f;
+    s_weff[c] = a.weff[(size_t)n * 64 + c];
+  }
+  __syncthreads();
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= a.V) return;
+  float e[C];
+  float g1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < C / 8; ++k) {
+    float f[8];
+    chunk_to_floats(ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = k * 8 + i;
+      const float t = lrelu_((f[i] - s_mean[c]) * s_rstd[c]);
+      e[c] = t;
+      g1 = fmaf(s_wse[c], t, g1);
+    }
+  }
+  g1 = sigmoidf_(g1);
+  float g2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) { e[c] *= g1; g2 = fmaf(s_wse2[c], e[c], g2); }
+  if (GATES == 2) {
+    g2 = sigmoidf_(g2);
+#pragma unroll
+    for (int c = 0; c < C; ++c) e[c] *= g2;
+  }
+  float t = a.wcst[n];
+#pragma unroll
+  for (int c = 0; c < C; ++c) t = fmaf(s_weff[c], e[c], t);
+  float* tp = a.T + (size_t)n * a.V + v;
+  *tp = a.t_init ? t : (*tp + t);
+  if (a.dest) {
+#pragma unroll
+    for (int k = 0; k < C / 8; ++k)
+      st_chunk(a.dest + (((size_t)n * a.dest_chunks + a.dest_off + k) * a.V + v) * 8, floats_to_chunk(e + k * 8));
+  }
+}
+
+template <int C>
+static int launch_apply_sse_c(int N, const SseArgs& a, cudaStream_t st) {
+  dim3 grid((unsigned)((a.V + 255) / 256), N);
+  if (a.wse2) apply_sse_kernel<C, 2><<<grid, 256, 0, st>>>(a);
+  else apply_sse_kernel<C, 1><<<grid, 256, 0, st>>>(a);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_apply_sse(int C, int N, const SseArgs& a, cudaStream_t st) {
+  switch (C) {
+    case 8: return launch_apply_sse_c<8>(N, a, st);
+    case 16: return launch_apply_sse_c<16>(N, a, st);
+    case 32: return launch_apply_sse_c<32>(N, a, st);
+    case 64: return launch_apply_sse_c<64>(N, a, st);
+  }
+  seunet_set_error("apply_sse: C=%d unsupported", C);
+  return 1;
+}
+
+// =============================================================================================
+// CAT block apply:  out = lrelu(IN(y)) [+ lrelu(IN(Wx x))]  -> full-res slot and/or 2x2x2 max-pool
+// (SE_UNet.py:45-49, 186-189, 195-198, 204-206, 212, 218, 224)
+// =============================================================================================
+template <int C, bool HASX, bool POOL>
+__global__ void __launch_bounds__(256) apply_cat_kernel(const __grid_constant__ CatArgs a) {
+  __shared__ float s_mean[8], s_rstd[8], s_mx[8], s_rx[8], s_wx[8][kMaxInCh];
+  const int n = blockIdx.z, k = blockIdx.y;
+  const long long V = dims_vox(a.d);
+  if (threadIdx.x < 8) {
+    const int c = k * 8 + threadIdx.x;
+    const double s = a.stats[((size_t)n * a.stats_c + c) * 2], q = a.stats[((size_t)n * a.stats_c + c) * 2 + 1];
+    const double mean = s / (double)V;
+    double var = q / (double)V - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)kInEps));
+    if (HASX) {
+      // analytic InstanceNorm statistics of the 1x1x1 conv of x: mean' = w.mu, var' = w^T Cov w
+      const double* m = a.mom + (size_t)n * kMomStride;
+      const double mu0 = m[0] / V, mu1 = m[1] / V;
+      const double c00 = m[2] / V - mu0 * mu0, c11 = m[3] / V - mu1 * mu1, c01 = m[4] / V - mu0 * mu1;
+      const double w0 = a.wx[c * a.in_ch], w1 = a.in_ch > 1 ? a.wx[c * a.in_ch + 1] : 0.0;
+      double vx = w0 * w0 * c00 + w1 * w1 * c11 + 2.0 * w0 * w1 * c01;
+      if (vx < 0) vx = 0;
+      s_mx[threadIdx.x] = (float)(w0 * mu0 + w1 * mu1);
+      s_rx[threadIdx.x] = (float)(1.0 / sqrt(vx + (double)kInEps));
+      s_wx[threadIdx.x][0] = (float)w0;
+      s_wx[threadIdx.x][1] = (float)w1;
+    }
+  }
+  __syncthreads();
+  const act_t* rawp = a.raw + ((size_t)n * a.raw_chunks + k) * V * 8;
+  auto eval = [&](long long v, int dz, int hy, int wx, float* o) {
+    float f[8];
+    chunk_to_floats(ld_chunk_stream(rawp + (size_t)v * 8), f);
+    float x0 = 0.f, x1 = 0.f;
+    if (HASX) {
+      const float* xp = a.x + n * a.xs[0] + dz * a.xs[2] + hy * a.xs[3] + wx * a.xs[4];
+      x0 = xp[0];
+      if (a.in_ch > 1) x1 = xp[a.xs[1]];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float r = lrelu_((f[i] - s_mean[i]) * s_rstd[i]);
+      if (HASX) r += lrelu_((fmaf(s_wx[i][0], x0, s_wx[i][1] * x1) - s_mx[i]) * s_rx[i]);
+      o[i] = r;
+    }
+  };
+  if (!POOL) {
+    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const int wx = (int)(v % a.d.W), hy = (int)((v / a.d.W) % a.d.H), dz = (int)(v / ((long long)a.d.W * a.d.H));
+    float o[8];
+    eval(v, dz, hy, wx, o);
+    if (a.dest) st_chunk(a.dest + (((size_t)n * a.dest_chunks + a.dest_off + k) * V + v) * 8, floats_to_chunk(o));
+  } else {
+    const int Dp = a.d.D >> 1, Hp = a.d.H >> 1, Wp = a.d.W >> 1;
+    const long long Vp = (long long)Dp * Hp * Wp;
+    const long long pv = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (pv >= Vp) return;
+    const int pw = (int)(pv % Wp), ph = (int)((pv / Wp) % Hp), pd = (int)(pv / ((long long)Wp * Hp));
+    float mx[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int dz = pd * 2 + (j >> 2), hy = ph * 2 + ((j >> 1) & 1), wx = pw * 2 + (j & 1);
+      const long long v = ((long long)dz * a.d.H + hy) * a.d.W + wx;
+      float o[8];
+      eval(v, dz, hy, wx, o);
+      if (a.dest) st_chunk(a.dest + (((size_t)n * a.dest_chunks + a.dest_off + k) * V + v) * 8, floats_to_chunk(o));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], o[i]);
+    }
+    st_chunk(a.pdest + (((size_t)n * a.pdest_chunks + a.pdest_off + k) * Vp + pv) * 8, floats_to_chunk(mx));
+  }
+}
+
+template <int C>
+static int launch_apply_cat_c(const CatArgs& a, cudaStream_t st) {
+  const long long V = dims_vox(a.d);
+  const bool pool = a.pdest != nullptr, hasx = a.x != nullptr;
+  const long long items = pool ? V / 8 : V;
+  dim3 grid((unsigned)((items + 255) / 256), C / 8, a.d.N);
+  if (hasx && pool) apply_cat_kernel<C, true, true><<<grid, 256, 0, st>>>(a);
+  else if (hasx) apply_cat_kernel<C, true, false><<<grid, 256, 0, st>>>(a);
+  else if (pool) apply_cat_kernel<C, false, true><<<grid, 256, 0, st>>>(a);
+  else apply_cat_kernel<C, false, false><<<grid, 256, 0, st>>>(a);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_apply_cat(int C, const CatArgs& a, cudaStream_t st) {
+  if (a.x && (a.in_ch < 1 || a.in_ch > kMaxInCh)) { seunet_set_error("apply_cat: in_ch unsupported"); return 1; }
+  switch (C) {
+    case 16: return launch_apply_cat_c<16>(a, st);
+    case 32: return launch_apply_cat_c<32>(a, st);
+    case 64: return launch_apply_cat_c<64>(a, st);
+  }
+  seunet_set_error("apply_cat: C=%d unsupported", C);
+  return 1;
+}
+
+// =============================================================================================
+// trilinear interpolation helpers, align_corners=True (ATen area_pixel_compute_source_index)
+// =============================================================================================
+struct Lerp { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lerp lerp_ac(int dst, int in_size, int out_size) {
+  const float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  const float src = scale * (float)dst;
+  Lerp r;
+  r.i0 = (int)src;
+  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) upsample2_kernel(const act_t* __restrict__ src, Dims sd, act_t* __restrict__ dst,
+                                                        int dst_chunks, int dst_off, int src_chunks) {
+  const int n = blockIdx.z, k = blockIdx.y;
+  const int Do = sd.D * 2, Ho = sd.H * 2, Wo = sd.W * 2;
+  const long long Vo = (long long)Do * Ho * Wo, Vs = dims_vox(sd);
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= Vo) return;
+  const int wx = (int)(v % Wo), hy = (int)((v / Wo) % Ho), dz = (int)(v / ((long long)Wo * Ho));
+  const Lerp ld = lerp_ac(dz, sd.D, Do), lh = lerp_ac(hy, sd.H, Ho), lw = lerp_ac(wx, sd.W, Wo);
+  const act_t* sp = src + ((size_t)n * src_chunks + k) * Vs * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int di = (j & 4) ? ld.i1 : ld.i0, hi = (j & 2) ? lh.i1 : lh.i0, wi = (j & 1) ? lw.i1 : lw.i0;
+    const float wgt = ((j & 4) ? ld.l1 : ld.l0) * ((j & 2) ? lh.l1 : lh.l0) * ((j & 1) ? lw.l1 : lw.l0);
+    float f[8];
+    chunk_to_floats(ld_chunk(sp + (((size_t)di * sd.H + hi) * sd.W + wi) * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, f[i], acc[i]);
+  }
+  st_chunk(dst + (((size_t)n * dst_chunks + dst_off + k) * Vo + v) * 8, floats_to_chunk(acc));
+}
+
+int launch_upsample2(const act_t* src, int C, Dims sd, act_t* dst, int dst_chunks, int dst_off, cudaStream_t st) {
+  const long long Vo = dims_vox(sd) * 8;
+  dim3 grid((unsigned)((Vo + 255) / 256), C / 8, sd.N);
+  upsample2_kernel<<<grid, 256, 0, st>>>(src, sd, dst, dst_chunks, dst_off, C / 8);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// folded head weights:  weff[blk][n][c] = sum_j hw[2k+j] * drop[n][2k+j] * W2[j][c]
+// (conv2 SE_UNet.py:33/80, DropLayer 89-97, dc0_0/dc0_1 232-233; all linear, so they commute
+//  with the trilinear up-sampling of the side branch)
+// =============================================================================================
+__global__ void headw_kernel(const float* __restrict__ params, const float* __restrict__ drop0,
+                             const float* __restrict__ drop1, const __grid_constant__ HeadwArgs a,
+                             float* __restrict__ weff, float* __restrict__ wcst) {
+  const int b = blockIdx.x, n = blockIdx.y, N = gridDim.y;
+  const HeadwBlock blk = a.blk[b];
+  const int hc = blk.head == 0 ? 24 : 12;
+  const float* drop = blk.head == 0 ? drop0 : drop1;
+  const float* hw = params + a.hw_off[blk.head];
+  const float h0 = hw[2 * blk.k] * drop[n * hc + 2 * blk.k];
+  const float h1 = hw[2 * blk.k + 1] * drop[n * hc + 2 * blk.k + 1];
+  const int c = threadIdx.x;
+  if (c < 64) {
+    float v = 0.f;
+    if (c < blk.C) v = h0 * params[blk.w2_off + c] + h1 * params[blk.w2_off + blk.C + c];
+    weff[((size_t)b * N + n) * 64 + c] = v;
+  }
+  if (c == 0) wcst[(size_t)b * N + n] = h0 * params[blk.b2_off] + h1 * params[blk.b2_off + 1];
+}
+
+int launch_headw(const float* params, const float* drop0, const float* drop1, int N, const HeadwArgs& a,
+                 float* weff, float* wcst, cudaStream_t st) {
+  dim3 grid(a.nblk, N);
+  headw_kernel<<<grid, 64, 0, st>>>(params, drop0, drop1, a, weff, wcst);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// head: pred = bias + T(S) + Up2(T(S/2)) + Up4(T(S/4)) [+ Up8(T(S/8))]
+// =============================================================================================
+__device__ __forceinline__ float sample_ac(const float* __restrict__ T, int Ds, int Hs, int Ws, int dz, int hy, int wx,
+                                           int Do, int Ho, int Wo) {
+  const Lerp ld = lerp_ac(dz, Ds, Do), lh = lerp_ac(hy, Hs, Ho), lw = lerp_ac(wx, Ws, Wo);
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int di = (j & 4) ? ld.i1 : ld.i0, hi = (j & 2) ? lh.i1 : lh.i0, wi = (j & 1) ? lw.i1 : lw.i0;
+    const float wgt = ((j & 4) ? ld.l1 : ld.l0) * ((j & 2) ? lh.l1 : lh.l0) * ((j & 1) ? lw.l1 : lw.l0);
+    acc = fmaf(wgt, __ldg(T + ((size_t)di * Hs + hi) * Ws + wi), acc);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256) head_kernel(const __grid_constant__ HeadArgs a) {
+  const int n = blockIdx.y;
+  const Dims d = a.d;
+  const long long V = dims_vox(d);
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const int wx = (int)(v % d.W), hy = (int)((v / d.W) % d.H), dz = (int)(v / ((long long)d.W * d.H));
+  float p0 = a.bias0[0] + a.T0[0][(size_t)n * V + v];
+  float p1 = a.bias1[0] + a.T1[0][(size_t)n * V + v];
+#pragma unroll
+  for (int l = 1; l < 4; ++l) {
+    const int Ds = d.D >> l, Hs = d.H >> l, Ws = d.W >> l;
+    const size_t Vs = (size_t)Ds * Hs * Ws;
+    p0 += sample_ac(a.T0[l] + n * Vs, Ds, Hs, Ws, dz, hy, wx, d.D, d.H, d.W);
+    if (l < 3) p1 += sample_ac(a.T1[l] + n * Vs, Ds, Hs, Ws, dz, hy, wx, d.D, d.H, d.W);
+  }
+  a.pred0[(size_t)n * V + v] = p0;
+  a.pred1[(size_t)n * V + v] = p1;
+}
+
+int launch_head(const HeadArgs& a, cudaStream_t st) {
+  const long long V = dims_vox(a.d);
+  dim3 grid((unsigned)((V + 255) / 256), a.d.N);
+  head_kernel<<<grid, 256, 0, st>>>(a);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,100 @@
+"""GPU parity of the drop-in SE_UNet.forward (C ABI seunet_forward) against the fp32 CPU oracle.
+
+Tolerances are BASELINE.json's: logits within 2e-2 max-abs of the fp32 reference, >= 99.9 % agreement of
+the thresholded masks (logit >= 0 <=> sigmoid >= 0.5, prediction.py:104-111).  With random-init weights
+logits sit near 0, so mask agreement is also reported on voxels with |logit_ref| > 2e-2 (SURVEY 8d hazard).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import seunet_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-2
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _model(in_ch, seed=777, train=False):
+    from se_unet_airseg_b200 import SE_UNet
+    sd = oracle.init_params(in_ch, 1, seed=seed)
+    m = SE_UNet(in_ch, 1)
+    missing = m.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    m = m.cuda()
+    m.train(train)
+    return m, sd
+
+
+def _compare(p, r, name):
+    err = (p - r).abs().max().item()
+    agree = ((p >= 0) == (r >= 0)).float().mean().item()
+    conf = r.abs() > LOGIT_TOL
+    agree_conf = ((p >= 0) == (r >= 0))[conf].float().mean().item() if conf.any() else 1.0
+    print(f"{name}: max|dlogit|={err:.3e} mask agreement={agree:.5f} (confident voxels: {agree_conf:.5f})")
+    assert err <= LOGIT_TOL, f"{name}: logits differ by {err}"
+    assert agree_conf >= 0.999
+    return err, agree
+
+
+@pytest.mark.parametrize("in_ch,shape", [(2, (1, 32, 32, 32)), (1, (1, 32, 32, 32)), (2, (2, 16, 32, 48)), (2, (1, 24, 40, 24))])
+def test_forward_eval_matches_oracle(in_ch, shape):
+    B, D, H, W = shape
+    m, sd = _model(in_ch)
+    g = torch.Generator().manual_seed(42)
+    x = torch.rand(B, in_ch, D, H, W, generator=g)
+    with torch.no_grad():
+        r0, r1 = oracle.forward(sd, x)
+        p0, p1 = m(x.cuda())
+    assert p0.dtype == torch.float32 and p0.shape == (B, 1, D, H, W)
+    _compare(p0.cpu(), r0, "pred0")
+    _compare(p1.cpu(), r1, "pred1")
+
+
+def test_forward_noncontiguous_input_view():
+    """prediction.py:102 feeds x[:, :, xl:xr, yl:yr, zl:zr] - a strided view - straight into the model."""
+    m, sd = _model(2)
+    g = torch.Generator().manual_seed(7)
+    big = torch.rand(1, 2, 40, 48, 40, generator=g)
+    view = big[:, :, 4:36, 8:40, 3:35]
+    with torch.no_grad():
+        r0, r1 = oracle.forward(sd, view.contiguous())
+        bigc = big.cuda()
+        p0, p1 = m(bigc[:, :, 4:36, 8:40, 3:35])
+    _compare(p0.cpu(), r0, "pred0")
+    _compare(p1.cpu(), r1, "pred1")
+
+
+def test_forward_train_mode_droplayer_matches_oracle():
+    """DropLayer is live in train mode (also in the reference's validation/test loops): same CPU-generator
+    draw order (dropout1 then dropout2, SE_UNet.py:232-233) => same mask => same logits."""
+    m, sd = _model(2, train=True)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 2, 16, 16, 16, generator=g)
+    torch.manual_seed(2024)
+    d0 = oracle.drop_scale(2, 24)
+    d1 = oracle.drop_scale(2, 12)
+    with torch.no_grad():
+        r0, r1 = oracle.forward(sd, x, d0, d1)
+        torch.manual_seed(2024)
+        p0, p1 = m(x.cuda())
+    _compare(p0.cpu(), r0, "pred0")
+    _compare(p1.cpu(), r1, "pred1")
+
+
+def test_forward_matches_golden_reference_vectors():
+    """tests/golden/forward_*.npz were produced by the UNMODIFIED reference module (oracle/make_golden.py)."""
+    files = sorted(f for f in os.listdir(GOLDEN) if f.startswith("forward_") and f.endswith(".npz"))
+    assert files, "golden vectors missing"
+    for f in files:
+        z = np.load(os.path.join(GOLDEN, f))
+        in_ch = int(z["in_channel"])
+        m, _ = _model(in_ch, seed=int(z["seed"]))
+        x = torch.from_numpy(z["x"])
+        with torch.no_grad():
+            p0, p1 = m(x.cuda())
+        _compare(p0.cpu(), torch.from_numpy(z["pred0"]), f + ":pred0")
+        _compare(p1.cpu(), torch.from_numpy(z["pred1"]), f + ":pred1")
