@@ -63,13 +63,24 @@ int seunet_pack_weights(seunet_plan_t* plan, const float* params, seunet_stream_
 /* SE_UNet.forward (SE_UNet.py:181-238).
  *   x        fp32, element strides x_strides[5] = (n, c, d, h, w)  (callers pass non-contiguous
  *            slices, prediction.py:102)
+ *   x_offsets HOST array of `batch` element offsets of each sample relative to x (sliding windows of
+ *            one resident CT volume batched into one forward), or NULL: sample n starts at n*x_strides[0]
  *   params   flat fp32 parameter buffer (see above)
  *   drop0/1  DropLayer scale factors r*C/(sum r + 0.01) of shape [batch][24] / [batch][12]
  *            (SE_UNet.py:89-97; all ones in eval mode) - drawn by the host module with the
  *            reference's CPU-generator semantics
  *   pred0/1  fp32 logits [batch][1][D][H][W], contiguous */
-int seunet_forward(seunet_plan_t* plan, const float* x, const int64_t* x_strides, const float* params,
-                   const float* drop0, const float* drop1, float* pred0, float* pred1, seunet_stream_t stream);
+int seunet_forward(seunet_plan_t* plan, const float* x, const int64_t* x_strides, const int64_t* x_offsets,
+                   const float* params, const float* drop0, const float* drop1, float* pred0, float* pred1,
+                   seunet_stream_t stream);
+
+/* Optional per-launch timing with CUDA events recorded on the caller's stream (bench roofline).
+ * After a forward and a stream synchronize: interval i covers the launches named by `label`
+ * ("conv:dc5", "apply:dc5", "cat:ec33", "up:d1", "head", "prep"); flops = algorithmic FLOPs of a
+ * conv interval (2*voxels*Cin*Cout*k^3), 0 otherwise. */
+int seunet_plan_set_timing(seunet_plan_t* plan, int on);
+int seunet_plan_timing_count(const seunet_plan_t* plan);
+int seunet_plan_timing_get(const seunet_plan_t* plan, int i, const char** label, float* ms, double* flops);
 
 /* ---- single-op entry points (parity tests and micro-benchmarks) --------------------------- */
 /* nn.Conv3d(Cin,Cout,k,padding=dil,dilation=dil) forward on chunk-plane activations
@@ -85,6 +96,19 @@ int seunet_to_chunks(const float* src, int N, int C, int D, int H, int W, void* 
                      seunet_stream_t stream);
 int seunet_from_chunks(const void* src, int src_chunks, int src_off, int N, int C, int D, int H, int W, float* dst,
                        seunet_stream_t stream);
+
+/* ---- sliding-window inference support (prediction.py:39-49, 69-111) ------- */
+/* two_channel(img + offset): img int16 (dtype 0) or fp32 (dtype 1) of nvox voxels -> out[2][nvox] fp32,
+ * HU windows [-1024,1024] and [-1000,500] scaled to [0,1]; evaluated in fp64 like the numpy reference. */
+int seunet_hu_windows(const void* img, int dtype, int64_t nvox, double offset, float* out, seunet_stream_t stream);
+/* acc[window b] += sigmoid(logits[b]) for B windows of size (cd,ch,cw) starting at HOST starts[b][3]
+ * inside the (X,Y,Z) fp32 accumulator volume (prediction.py:103-106). */
+int seunet_window_accumulate(const float* logits, const int* starts, int B, int cd, int ch, int cw, float* acc, int X,
+                             int Y, int Z, int apply_sigmoid, seunet_stream_t stream);
+/* mean = acc / count (prediction.py:109), mask = mean >= threshold. counts_dev: DEVICE int[X+Y+Z] with the
+ * per-axis window coverage counts. mask may be NULL; write_mean stores the mean back into acc. */
+int seunet_window_finalize(float* acc, const int* counts_dev, int X, int Y, int Z, float threshold,
+                           unsigned char* mask, int write_mean, seunet_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -254,3 +254,24 @@ def two_channel(img_hu):
     a = (img_hu.clamp(-1024.0, 1024.0) + 1024.0) / 2048.0
     b = (img_hu.clamp(-1000.0, 500.0) + 1000.0) / 1500.0
     return torch.stack((a, b), 0)
+
+
+def predict_volume(sd, img_stored, cube=128, step=64):
+    """prediction.py:65-111 up to the 0.5 threshold: img_stored holds the stored CT values (HU + 1024);
+    returns (mean probability float64 volume, mask).  Eval mode like prediction.py:64."""
+    import numpy as np
+    img = img_stored.to(torch.float64) - 1024                                       # :69
+    x = two_channel(img).to(torch.float32).unsqueeze(0)                            # :72-77
+    X, Y, Z = img.shape
+    pred = np.zeros((X, Y, Z))
+    pred_num = np.zeros((X, Y, Z))
+    with torch.no_grad():
+        for xl in window_starts(X, cube, step):                                    # :83-100
+            for yl in window_starts(Y, cube, step):
+                for zl in window_starts(Z, cube, step):
+                    _p0, p = forward(sd, x[:, :, xl:xl + cube, yl:yl + cube, zl:zl + cube])   # :102-103
+                    p = torch.sigmoid(p).numpy()[0, 0]                             # :104-105
+                    pred[xl:xl + cube, yl:yl + cube, zl:zl + cube] += p            # :106
+                    pred_num[xl:xl + cube, yl:yl + cube, zl:zl + cube] += 1        # :107
+    pred = pred / pred_num                                                         # :109
+    return pred, (pred >= 0.5)

@@ -150,8 +150,8 @@ class _SEUNetFunction(torch.autograd.Function):
         pred0 = torch.empty((B, module.n_classes, D, H, W), dtype=torch.float32, device=x.device)
         pred1 = torch.empty_like(pred0)
         strides = (ctypes.c_int64 * 5)(*x.stride())
-        _lib.check(L.seunet_forward(plan.handle, _lib.ptr(x), strides, _lib.ptr(flat), _lib.ptr(drop0), _lib.ptr(drop1),
-                                    _lib.ptr(pred0), _lib.ptr(pred1), _lib.stream_ptr()), "seunet_forward")
+        _lib.check(L.seunet_forward(plan.handle, _lib.ptr(x), strides, None, _lib.ptr(flat), _lib.ptr(drop0),
+                                    _lib.ptr(drop1), _lib.ptr(pred0), _lib.ptr(pred1), _lib.stream_ptr()), "seunet_forward")
         ctx.module, ctx.plan = module, plan
         ctx.save_for_backward(x, flat, drop0, drop1)
         ctx.shapes = [p.shape for p in params]
@@ -340,7 +340,7 @@ class SE_UNet(nn.Module):
             pred0 = torch.empty((B, self.n_classes, D, H, W), dtype=torch.float32, device=x.device)
             pred1 = torch.empty_like(pred0)
             strides = (ctypes.c_int64 * 5)(*x.stride())
-            _lib.check(L.seunet_forward(plan.handle, _lib.ptr(x), strides, _lib.ptr(flat), _lib.ptr(drop0),
+            _lib.check(L.seunet_forward(plan.handle, _lib.ptr(x), strides, None, _lib.ptr(flat), _lib.ptr(drop0),
                                         _lib.ptr(drop1), _lib.ptr(pred0), _lib.ptr(pred1), _lib.stream_ptr()),
                        "seunet_forward")
             return pred0, pred1

@@ -158,7 +158,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     }
   } else if (warp == 1) {
     // =================================== UMMA issuer ===================================
-    if (lane == 0) {
+    // The whole warp runs this loop with warp-uniform control flow so that descriptors live in
+    // uniform registers; only the tcgen05.mma / tcgen05.commit themselves are issued by one elected lane.
+    {
       uint32_t st = 0, ph = 0, wcount = 0, acc = 0, accph = 0, wready = 0;
       const uint32_t idesc1 = umma_idesc(SEUNET_UMMA_FMT, 128, COUT);
       const uint32_t idesc2 = umma_idesc(SEUNET_UMMA_FMT, 128, 2 * COUT);
@@ -189,31 +191,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             const uint32_t idesc = nj == 3 ? idesc3 : (nj == 2 ? idesc2 : idesc1);
             mbar_wait(full_bar(st), ph);
             tc_fence_after();
-            const uint32_t a_addr = s_addr + st * a.stage_bytes;
-            const uint32_t b_addr = wsm + jlo * COUT * 16;
-            for (int s = 0; s < a.nsteps; ++s) {
-              const ConvStep stp = a.steps[s];
-              const uint64_t adesc = umma_desc(a_addr + stp.a_off, stp.a_lbo, a.a_sbo);
-              if (c == 0 && s == 0) {
-                // first contribution of this input plane: the stacked accumulators may differ in
-                // whether they were written before, so issue one N=COUT instruction per plane.
-                for (int jj = 0; jj < nj; ++jj) {
-                  const int sl = slot_lo + jj;
-                  const uint64_t bdesc = umma_desc(b_addr + stp.b_off + jj * COUT * 16, a.b_lbo, 128);
-                  umma_f16(dcol + jj * COUT, adesc, bdesc, idesc1, (touched >> sl) & 1u);
-                  touched |= 1u << sl;
-                }
-              } else {
-                const uint64_t bdesc = umma_desc(b_addr + stp.b_off, a.b_lbo, 128);
-                umma_f16(dcol, adesc, bdesc, idesc, 1u);
+            const uint64_t abase = umma_desc(s_addr + st * a.stage_bytes, 0, a.a_sbo);
+            const uint64_t bbase = umma_desc(wsm + jlo * COUT * 16, a.b_lbo, 128);
+            int s0 = 0;
+            if (c == 0) {
+              // first contribution of this input plane: the stacked accumulators may differ in
+              // whether they were written before, so issue one N=COUT instruction per plane.
+              const uint64_t adesc = abase + a.a_delta[0];
+              for (int jj = 0; jj < nj; ++jj) {
+                const int sl = slot_lo + jj;
+                const uint64_t bdesc = bbase + a.b_delta[0] + (uint64_t)(jj * COUT);
+                if (elect_one_sync()) umma_f16(dcol + jj * COUT, adesc, bdesc, idesc1, (touched >> sl) & 1u);
+                touched |= 1u << sl;
               }
+              s0 = 1;
             }
-            umma_commit(empty_bar(st));  // frees the activation stage when these MMAs retire
+#pragma unroll 4
+            for (int s = s0; s < a.nsteps; ++s) {
+              const uint64_t adesc = abase + a.a_delta[s];
+              const uint64_t bdesc = bbase + a.b_delta[s];
+              if (elect_one_sync()) umma_f16(dcol, adesc, bdesc, idesc, 1u);
+            }
+            if (elect_one_sync()) umma_commit(empty_bar(st));  // frees the activation stage when these MMAs retire
+            __syncwarp();
             if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
           }
-          if (!resident) { umma_commit(wempty_bar(slot)); ++wcount; }
+          if (!resident) {
+            if (elect_one_sync()) umma_commit(wempty_bar(slot));
+            __syncwarp();
+            ++wcount;
+          }
         }
-        umma_commit(tfull_bar(acc));
+        if (elect_one_sync()) umma_commit(tfull_bar(acc));
+        __syncwarp();
         acc ^= 1u;
         if (acc == 0) accph ^= 1u;
       }
@@ -458,6 +468,8 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
       cs.a_lbo = a_lbo;
     }
     cs.b_off = (uint32_t)s * 2u * nkd * g.COUT * 16u;
+    a.a_delta[s] = (uint64_t)(cs.a_off >> 4) | ((uint64_t)(cs.a_lbo >> 4) << 16);
+    a.b_delta[s] = (uint64_t)(cs.b_off >> 4);
   }
   if (in_chunk_off + g.Cin / 8 > in_chunks_total) { seunet_set_error("conv: input slice exceeds buffer"); return 1; }
   if (out_chunk_off + g.COUT / 8 > out_chunks_total) { seunet_set_error("conv: output slice exceeds buffer"); return 1; }

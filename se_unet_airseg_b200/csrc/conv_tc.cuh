@@ -33,6 +33,8 @@ struct ConvKArgs {
   act_t* out;            // raw conv output, chunk-plane layout
   double* stats;         // [N][COUT][2] running (sum, sum of squares), fp64 atomics
   ConvStep steps[kConvMaxSteps];
+  uint64_t a_delta[kConvMaxSteps];   // per-step additive delta of the A smem descriptor (addr | lbo<<16)
+  uint64_t b_delta[kConvMaxSteps];   // per-step additive delta of the B smem descriptor
 };
 
 // How the fp32 reference weights map into one UMMA K=16 step of the packed image.

@@ -148,6 +148,19 @@ struct seunet_plan {
   HeadwArgs headw;
   uint8_t* ws = nullptr;
   uint8_t* wimg = nullptr;
+  XOffsets xo;                      // per-sample input offsets of the current forward
+  // optional per-launch CUDA-event timing (bench roofline); events live on the caller's stream
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<std::string> ev_label;
+  std::vector<double> ev_flops;
+  size_t ev_n = 0;
+  void mark(const char* label, cudaStream_t st, double flops = 0.0) {
+    if (!timing) return;
+    if (ev_n >= ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); ev_label.emplace_back(); ev_flops.push_back(0.0); }
+    ev_label[ev_n] = label; ev_flops[ev_n] = flops;
+    cudaEventRecord(ev[ev_n++], st);
+  }
   Dims dims(int level) const { return Dims{N, D >> level, H >> level, W >> level}; }
   long long vox(int level) const { return (long long)(D >> level) * (H >> level) * (W >> level); }
 };
@@ -279,7 +292,21 @@ extern "C" int seunet_plan_create(seunet_plan_t** out, int batch, int D, int H, 
   return 0;
 }
 
-extern "C" void seunet_plan_destroy(seunet_plan_t* p) { delete p; }
+extern "C" void seunet_plan_destroy(seunet_plan_t* p) {
+  if (!p) return;
+  for (auto e : p->ev) cudaEventDestroy(e);
+  delete p;
+}
+extern "C" int seunet_plan_set_timing(seunet_plan_t* p, int on) { if (!p) return 1; p->timing = on != 0; p->ev_n = 0; return 0; }
+extern "C" int seunet_plan_timing_count(const seunet_plan_t* p) { return p && p->ev_n ? (int)p->ev_n - 1 : 0; }
+// Interval i = time between mark i and mark i+1 (the launches issued after mark i), label/flops of mark i+1.
+extern "C" int seunet_plan_timing_get(const seunet_plan_t* p, int i, const char** label, float* ms, double* flops) {
+  if (!p || i < 0 || i + 1 >= (int)p->ev_n) { seunet_set_error("timing_get: index out of range"); return 1; }
+  SEUNET_CUDA_CHECK(cudaEventElapsedTime(ms, p->ev[i], p->ev[i + 1]));
+  *label = p->ev_label[i + 1].c_str();
+  *flops = p->ev_flops[i + 1];
+  return 0;
+}
 extern "C" size_t seunet_plan_workspace_bytes(const seunet_plan_t* p) { return p ? p->ws_bytes : 0; }
 extern "C" size_t seunet_plan_wimg_bytes(const seunet_plan_t* p) { return p ? p->wimg_bytes : 0; }
 
@@ -332,6 +359,7 @@ static int run_sse(seunet_plan* p, int i, const float* params, cudaStream_t st) 
   const SseDesc& s = kSse[i];
   ConvSlot& cs = p->sse_conv[i];
   if (conv_launch_run(cs.L, st)) return 1;
+  p->mark((std::string("conv:") + s.name).c_str(), st, 2.0 * p->N * p->vox(s.level) * cs.g.Cin_real * cs.g.Cout_real * 27.0);
   SseArgs a;
   memset(&a, 0, sizeof(a));
   a.raw = (const act_t*)(p->ws + cs.raw_off); a.raw_chunks = cs.g.COUT / 8;
@@ -347,13 +375,16 @@ static int run_sse(seunet_plan* p, int i, const float* params, cudaStream_t st) 
   if (s.out_buf != B_NONE) {
     a.dest = (act_t*)(p->ws + p->buf_off[s.out_buf]); a.dest_chunks = kBufs[s.out_buf].chunks; a.dest_off = s.out_off;
   }
-  return launch_apply_sse(s.cout, p->N, a, st);
+  if (launch_apply_sse(s.cout, p->N, a, st)) return 1;
+  p->mark((std::string("apply:") + s.name).c_str(), st);
+  return 0;
 }
 
 static int run_cat(seunet_plan* p, int i, const float* params, const float* x, const int64_t* xs, cudaStream_t st) {
   const CatDesc& c = kCat[i];
   ConvSlot& cs = p->cat_conv[i];
   if (conv_launch_run(cs.L, st)) return 1;
+  p->mark((std::string("conv:") + c.name).c_str(), st, 2.0 * p->N * p->vox(c.level) * cs.g.Cin_real * cs.g.Cout_real);
   CatArgs a;
   memset(&a, 0, sizeof(a));
   a.raw = (const act_t*)(p->ws + cs.raw_off); a.raw_chunks = cs.g.COUT / 8;
@@ -366,6 +397,7 @@ static int run_cat(seunet_plan* p, int i, const float* params, const float* x, c
     if (c.level == 0) {
       a.x = x;
       for (int k = 0; k < 5; ++k) a.xs[k] = xs[k];
+      a.xo = p->xo;
     } else {
       a.x = (const float*)(p->ws + (c.level == 1 ? p->xp1_off : p->xp2_off));
       const long long V = p->vox(c.level);
@@ -376,22 +408,33 @@ static int run_cat(seunet_plan* p, int i, const float* params, const float* x, c
   if (c.pool_buf != B_NONE) {
     a.pdest = (act_t*)(p->ws + p->buf_off[c.pool_buf]); a.pdest_chunks = kBufs[c.pool_buf].chunks; a.pdest_off = 0;
   }
-  return launch_apply_cat(c.cout, a, st);
+  if (launch_apply_cat(c.cout, a, st)) return 1;
+  p->mark((std::string("cat:") + c.name).c_str(), st);
+  return 0;
 }
 
-extern "C" int seunet_forward(seunet_plan_t* p, const float* x, const int64_t* xs, const float* params,
-                              const float* drop0, const float* drop1, float* pred0, float* pred1,
+extern "C" int seunet_forward(seunet_plan_t* p, const float* x, const int64_t* xs, const int64_t* x_offsets,
+                              const float* params, const float* drop0, const float* drop1, float* pred0, float* pred1,
                               seunet_stream_t stream) {
   if (!p || !p->ws) { seunet_set_error("forward: plan not bound"); return 1; }
   if (!x || !xs || !params || !drop0 || !drop1 || !pred0 || !pred1) { seunet_set_error("forward: null argument"); return 1; }
   cudaStream_t st = (cudaStream_t)stream;
   auto act = [&](int b) { return (act_t*)(p->ws + p->buf_off[b]); };
+  memset(&p->xo, 0, sizeof(p->xo));
+  if (x_offsets) {
+    if (p->N > kMaxWindowBatch) { seunet_set_error("forward: x_offsets supports at most %d samples", kMaxWindowBatch); return 1; }
+    p->xo.use = 1;
+    for (int n = 0; n < p->N; ++n) p->xo.off[n] = x_offsets[n];
+  }
+  p->ev_n = 0;
+  p->mark("start", st);
   SEUNET_CUDA_CHECK(cudaMemsetAsync(p->ws + p->stats_off, 0, p->stats_bytes, st));
   long long xs_ll[5];
   for (int k = 0; k < 5; ++k) xs_ll[k] = xs[k];
-  if (launch_input_prep(x, xs_ll, p->in_ch, p->dims(0), act(B_XB), (float*)(p->ws + p->xp1_off),
+  if (launch_input_prep(x, xs_ll, p->xo, p->in_ch, p->dims(0), act(B_XB), (float*)(p->ws + p->xp1_off),
                         (float*)(p->ws + p->xp2_off), (double*)(p->ws + p->mom_off), st)) return 1;
   if (launch_headw(params, drop0, drop1, p->N, p->headw, (float*)(p->ws + p->weff_off), (float*)(p->ws + p->wcst_off), st)) return 1;
+  p->mark("prep", st);
   // encoder, level 0 (SE_UNet.py:183-189)
   if (run_sse(p, S_EC1, params, st) || run_sse(p, S_EC2, params, st) || run_sse(p, S_EC3, params, st)) return 1;
   if (run_cat(p, C_EC33, params, x, xs, st)) return 1;
@@ -406,12 +449,15 @@ extern "C" int seunet_forward(seunet_plan_t* p, const float* x, const int64_t* x
   if (run_cat(p, C_EC123, params, x, xs, st)) return 1;
   // decoder (214-229)
   if (launch_upsample2(act(B_E7F), 64, p->dims(3), act(B_DC1IN), kBufs[B_DC1IN].chunks, 0, st)) return 1;
+  p->mark("up:e7", st);
   if (run_sse(p, S_DC1, params, st) || run_sse(p, S_DC2, params, st)) return 1;
   if (run_cat(p, C_DC22, params, x, xs, st)) return 1;
   if (launch_upsample2(act(B_D0F), 64, p->dims(2), act(B_DC3IN), kBufs[B_DC3IN].chunks, 0, st)) return 1;
+  p->mark("up:d0", st);
   if (run_sse(p, S_DC3, params, st) || run_sse(p, S_DC4, params, st)) return 1;
   if (run_cat(p, C_DC42, params, x, xs, st)) return 1;
   if (launch_upsample2(act(B_D1F), 32, p->dims(1), act(B_DC5IN), kBufs[B_DC5IN].chunks, 0, st)) return 1;
+  p->mark("up:d1", st);
   if (run_sse(p, S_DC5, params, st) || run_sse(p, S_DC6, params, st)) return 1;
   // dc62 (SE_UNet.py:230) is dead code in the reference: its result is never used.
   // heads (232-233)
@@ -423,7 +469,9 @@ extern "C" int seunet_forward(seunet_plan_t* p, const float* x, const int64_t* x
   h.bias0 = params + p->pt.off("dc0_0.bias");
   h.bias1 = params + p->pt.off("dc0_1.bias");
   h.pred0 = pred0; h.pred1 = pred1;
-  return launch_head(h, st);
+  if (launch_head(h, st)) return 1;
+  p->mark("head", st);
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -15,10 +15,12 @@ constexpr float kInEps = 1e-5f;   // nn.InstanceNorm3d default eps (SE_UNet.py:1
 // to the first/second moments of x at each level (used for the analytic InstanceNorm statistics of
 // the x33/x63/x93 injection branches).
 __global__ void __launch_bounds__(128) input_prep_kernel(const float* __restrict__ x, long long sN, long long sC, long long sD,
-                                                         long long sH, long long sW, int in_ch, Dims d,
+                                                         long long sH, long long sW, const __grid_constant__ XOffsets xo,
+                                                         int in_ch, Dims d,
                                                          act_t* __restrict__ xb, float* __restrict__ xp1,
                                                          float* __restrict__ xp2, double* __restrict__ mom) {
   const int n = blockIdx.y;
+  const long long xbase = xo.use ? xo.off[n] : n * sN;
   const int D4 = d.D >> 2, H4 = d.H >> 2, W4 = d.W >> 2;
   const long long nb = (long long)D4 * H4 * W4;
   const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(128) input_prep_kernel(const float* __restrict
             float v[kMaxInCh];
 #pragma unroll
             for (int c = 0; c < kMaxInCh; ++c)
-              v[c] = c < in_ch ? x[n * sN + c * sC + dz * sD + hy * sH + wx * sW] : 0.f;
+              v[c] = c < in_ch ? x[xbase + c * sC + dz * sD + hy * sH + wx * sW] : 0.f;
             float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c = 0; c < kMaxInCh; ++c) { f[c] = v[c]; p1[c] = fmaxf(p1[c], v[c]); }
@@ -86,14 +88,14 @@ __global__ void __launch_bounds__(128) input_prep_kernel(const float* __restrict
   }
 }
 
-int launch_input_prep(const float* x, const long long* xs, int in_ch, Dims d, act_t* xb, float* xp1, float* xp2,
+int launch_input_prep(const float* x, const long long* xs, const XOffsets& xo, int in_ch, Dims d, act_t* xb, float* xp1, float* xp2,
                       double* mom, cudaStream_t st) {
   if (in_ch < 1 || in_ch > kMaxInCh) { seunet_set_error("in_channel %d unsupported (1..%d)", in_ch, kMaxInCh); return 1; }
   if ((d.D | d.H | d.W) & 7) { seunet_set_error("spatial dims must be multiples of 8"); return 1; }
   SEUNET_CUDA_CHECK(cudaMemsetAsync(mom, 0, sizeof(double) * 3 * d.N * kMomStride, st));
   const long long nb = (long long)(d.D / 4) * (d.H / 4) * (d.W / 4);
   dim3 grid((unsigned)((nb + 127) / 128), d.N);
-  input_prep_kernel<<<grid, 128, 0, st>>>(x, xs[0], xs[1], xs[2], xs[3], xs[4], in_ch, d, xb, xp1, xp2, mom);
+  input_prep_kernel<<<grid, 128, 0, st>>>(x, xs[0], xs[1], xs[2], xs[3], xs[4], xo, in_ch, d, xb, xp1, xp2, mom);
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(256) apply_cat_kernel(const __grid_constant__ 
     chunk_to_floats(ld_chunk_stream(rawp + (size_t)v * 8), f);
     float x0 = 0.f, x1 = 0.f;
     if (HASX) {
-      const float* xp = a.x + n * a.xs[0] + dz * a.xs[2] + hy * a.xs[3] + wx * a.xs[4];
+      const float* xp = a.x + (a.xo.use ? a.xo.off[n] : n * a.xs[0]) + dz * a.xs[2] + hy * a.xs[3] + wx * a.xs[4];
       x0 = xp[0];
       if (a.in_ch > 1) x1 = xp[a.xs[1]];
     }

@@ -6,11 +6,15 @@ constexpr int kMaxInCh = 2;     // reference callers use in_channel=2 (default c
 constexpr int kMomStride = 8;   // doubles per (level, sample): sum x_i (2), sum x_i x_j (3), pad
 
 struct Dims { int N, D, H, W; };
+// Per-sample element offsets of the network input inside a larger tensor (sliding windows of one CT
+// volume, prediction.py:102).  use == 0: sample n starts at n * (sample stride).
+constexpr int kMaxWindowBatch = 32;
+struct XOffsets { int use; long long off[kMaxWindowBatch]; };
 __host__ __device__ inline long long dims_vox(const Dims& d) { return (long long)d.D * d.H * d.W; }
 
 // x (fp32, arbitrary strides) -> XB (storage type, 1 chunk plane, channels >= in_ch zero),
 // max-pooled fp32 copies at 1/2 and 1/4 resolution, and first/second moments at all three levels.
-int launch_input_prep(const float* x, const long long* xstride /*n,c,d,h,w in elements*/, int in_ch, Dims d,
+int launch_input_prep(const float* x, const long long* xstride /*n,c,d,h,w in elements*/, const XOffsets& xo, int in_ch, Dims d,
                       act_t* xb, float* xp1, float* xp2, double* mom /*[3][N][kMomStride]*/, cudaStream_t st);
 
 struct SseArgs {
@@ -29,7 +33,7 @@ struct CatArgs {
   const double* stats; int stats_c;
   Dims d;                                   // resolution of this block
   // optional injection branch lrelu(IN(Wx * x)) (SE_UNet.py:187,196,205)
-  const float* x; long long xs[5]; int in_ch; const float* wx; const double* mom;
+  const float* x; long long xs[5]; XOffsets xo; int in_ch; const float* wx; const double* mom;
   act_t* dest; int dest_chunks; int dest_off;       // full-resolution destination (may be null)
   act_t* pdest; int pdest_chunks; int pdest_off;    // 2x2x2 max-pooled destination (may be null)
 };

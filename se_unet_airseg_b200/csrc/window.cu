@@ -1,0 +1,89 @@
+// Sliding-window inference support kernels: HU windowing of the CT volume,
+// device-side overlap accumulation of window probabilities, mean + threshold.
+// Reference: prediction.py:39-49, 69-111.
+#include "../../include/seunet_b200.h"
+#include "common.cuh"
+
+// prediction.py:69 (img - 1024) and two_channel() (prediction.py:39-49), evaluated in float64 exactly
+// like the numpy reference and rounded once to fp32 (x = torch.from_numpy(img.astype(np.float32))).
+template <typename T>
+__global__ void __launch_bounds__(256) hu_windows_kernel(const T* __restrict__ img, long long n, double offset,
+                                                         float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = (double)img[i] + offset;
+    const double a = fmin(fmax(v, -1024.0), 1024.0);
+    const double b = fmin(fmax(v, -1000.0), 500.0);
+    out[i] = (float)((a + 1024.0) / 2048.0);
+    out[n + i] = (float)((b + 1000.0) / 1500.0);
+  }
+}
+
+extern "C" int seunet_hu_windows(const void* img, int dtype, int64_t nvox, double offset, float* out,
+                                 seunet_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (int)((nvox + 255) / 256 < 148 * 16 ? (nvox + 255) / 256 : 148 * 16);
+  if (dtype == 0) hu_windows_kernel<short><<<blocks, 256, 0, st>>>((const short*)img, nvox, offset, out);
+  else if (dtype == 1) hu_windows_kernel<float><<<blocks, 256, 0, st>>>((const float*)img, nvox, offset, out);
+  else { seunet_set_error("hu_windows: dtype %d unsupported (0=int16, 1=float32)", dtype); return 1; }
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+struct WinStarts { int n; int s[32][3]; };
+
+// pred[..window..] += sigmoid(logits)   (prediction.py:103-106; pred_num is analytic, see finalize)
+__global__ void __launch_bounds__(256) window_accumulate_kernel(const float* __restrict__ logits, const __grid_constant__ WinStarts ws,
+                                                                int cd, int ch, int cw, float* __restrict__ acc, int X, int Y,
+                                                                int Z, int apply_sigmoid) {
+  const int b = blockIdx.y;
+  const long long V = (long long)cd * ch * cw;
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const int w = (int)(v % cw), h = (int)((v / cw) % ch), d = (int)(v / ((long long)cw * ch));
+  float p = logits[(size_t)b * V + v];
+  if (apply_sigmoid) p = 1.f / (1.f + expf(-p));
+  atomicAdd(acc + ((size_t)(ws.s[b][0] + d) * Y + (ws.s[b][1] + h)) * Z + ws.s[b][2] + w, p);
+}
+
+extern "C" int seunet_window_accumulate(const float* logits, const int* starts /*host [B][3]*/, int B, int cd, int ch,
+                                        int cw, float* acc, int X, int Y, int Z, int apply_sigmoid,
+                                        seunet_stream_t stream) {
+  if (B < 1 || B > 32) { seunet_set_error("window_accumulate: batch %d out of range (1..32)", B); return 1; }
+  WinStarts ws;
+  ws.n = B;
+  for (int b = 0; b < B; ++b)
+    for (int k = 0; k < 3; ++k) {
+      ws.s[b][k] = starts[b * 3 + k];
+      const int lim = k == 0 ? X - cd : (k == 1 ? Y - ch : Z - cw);
+      if (ws.s[b][k] < 0 || ws.s[b][k] > lim) { seunet_set_error("window_accumulate: window %d out of bounds", b); return 1; }
+    }
+  const long long V = (long long)cd * ch * cw;
+  dim3 grid((unsigned)((V + 255) / 256), B);
+  window_accumulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, ws, cd, ch, cw, acc, X, Y, Z, apply_sigmoid);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// mean = acc / count (prediction.py:109) and mask = mean >= threshold.  count[x][y][z] is the product of the
+// per-axis window coverage counts (the windows form a full grid, prediction.py:83-100).
+__global__ void __launch_bounds__(256) window_finalize_kernel(float* __restrict__ acc, const int* __restrict__ cx,
+                                                              const int* __restrict__ cy, const int* __restrict__ cz, int X,
+                                                              int Y, int Z, float thr, unsigned char* __restrict__ mask,
+                                                              int write_mean) {
+  const long long V = (long long)X * Y * Z;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < V; i += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)(i % Z), y = (int)((i / Z) % Y), x = (int)(i / ((long long)Z * Y));
+    const float cnt = (float)(cx[x] * cy[y] * cz[z]);
+    const float m = acc[i] / cnt;
+    if (write_mean) acc[i] = m;
+    if (mask) mask[i] = m >= thr ? 1 : 0;
+  }
+}
+
+extern "C" int seunet_window_finalize(float* acc, const int* counts_dev /*device [X+Y+Z]*/, int X, int Y, int Z,
+                                      float threshold, unsigned char* mask, int write_mean, seunet_stream_t stream) {
+  window_finalize_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(acc, counts_dev, counts_dev + X, counts_dev + X + Y, X, Y,
+                                                                     Z, threshold, mask, write_mean);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

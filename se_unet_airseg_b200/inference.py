@@ -1,0 +1,135 @@
+"""GPU sliding-window inference driver, the B200-native counterpart of the loop in
+the reference's prediction.py:65-111:
+
+    img - 1024 -> two HU windows -> 128^3 windows at stride 64 (last window clamped) -> SE_UNet forward
+    (eval mode) -> sigmoid -> overlap mean -> >= 0.5
+
+Differences in HOW (not WHAT): the windows of one resident volume are batched into one forward (the C ABI
+takes per-sample offsets into the volume, no gather copy), probabilities are accumulated on the device in
+fp32 and the window-count volume is analytic; only the final mask crosses PCIe.  Post-processing after the
+threshold (double-threshold iteration, border crop, largest component - prediction.py:110-116) is CPU
+topology code outside this hot path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def window_starts(length, cube=128, step=64):
+    """Window origins along one axis, exactly prediction.py:80-100 (the last window is clamped)."""
+    if length < cube:
+        raise ValueError(f"axis of length {length} is shorter than the window ({cube})")
+    if (length - cube) % step == 0:
+        n = (length - cube) // step + 1
+    else:
+        n = (length - cube) // step + 2
+    out = []
+    for i in range(n):
+        lo = i * step
+        if lo + cube > length:
+            lo = length - cube
+        out.append(lo)
+    return out
+
+
+def coverage_counts(length, starts, cube):
+    c = np.zeros(length, dtype=np.int32)
+    for s in starts:
+        c[s:s + cube] += 1
+    return c
+
+
+class SlidingWindowPredictor:
+    """Runs `model` (se_unet_airseg_b200.SE_UNet on a CUDA device, eval mode like prediction.py:64) over a CT volume."""
+
+    def __init__(self, model, cube=128, step=64, batch=6, threshold=0.5):
+        self.model = model
+        self.cube, self.step, self.batch, self.threshold = cube, step, batch, threshold
+        self._geom = None
+
+    def _geometry(self, shape, device):
+        if self._geom is not None and self._geom[0] == (tuple(shape), device):
+            return self._geom[1]
+        X, Y, Z = shape
+        sx, sy, sz = (window_starts(n, self.cube, self.step) for n in (X, Y, Z))
+        wins = [(a, b, c) for a in sx for b in sy for c in sz]  # same nesting order as prediction.py:83-100
+        counts = np.concatenate([coverage_counts(X, sx, self.cube), coverage_counts(Y, sy, self.cube),
+                                 coverage_counts(Z, sz, self.cube)]).astype(np.int32)
+        g = dict(wins=wins, counts=torch.from_numpy(counts).to(device),
+                 acc=torch.empty((X, Y, Z), dtype=torch.float32, device=device),
+                 mask=torch.empty((X, Y, Z), dtype=torch.uint8, device=device),
+                 x2=torch.empty((1, 2, X, Y, Z), dtype=torch.float32, device=device))
+        self._geom = ((tuple(shape), device), g)
+        return g
+
+    @torch.no_grad()
+    def predict_device(self, img_dev, hu_offset=-1024.0, return_prob=False):
+        """img_dev: (X, Y, Z) int16 or fp32 CUDA tensor holding the stored CT values (HU + 1024, prediction.py:68-69).
+        Returns the uint8 mask (X, Y, Z) on the device (and the mean probability if return_prob)."""
+        L = _lib.lib()
+        m = self.model
+        if m.in_channel != 2:
+            raise ValueError("sliding-window CT inference needs the two-HU-window model (in_channel=2)")
+        if m.training:
+            raise RuntimeError("SlidingWindowPredictor mirrors prediction.py: call model.eval() first")
+        dev = img_dev.device
+        X, Y, Z = img_dev.shape
+        g = self._geometry((X, Y, Z), dev)
+        st = _lib.stream_ptr()
+        dtype = {torch.int16: 0, torch.float32: 1}[img_dev.dtype]
+        img_dev = img_dev.contiguous()
+        _lib.check(L.seunet_hu_windows(_lib.ptr(img_dev), dtype, X * Y * Z, float(hu_offset), _lib.ptr(g["x2"]), st),
+                   "seunet_hu_windows")
+        g["acc"].zero_()
+        x2 = g["x2"]
+        sN, sC, sD, sH, sW = x2.stride()
+        cube = self.cube
+        wins = g["wins"]
+        params = m._param_tensors()
+        flat = m._flat_params(params)
+        i = 0
+        while i < len(wins):
+            b = min(self.batch, len(wins) - i)
+            plan = m._plan(b, cube, cube, cube, 0, dev)
+            plan.pack(flat)
+            ones0, ones1, pred0, pred1 = self._buffers(plan, b, dev)
+            offs = (ctypes.c_int64 * b)(*[w[0] * sD + w[1] * sH + w[2] * sW for w in wins[i:i + b]])
+            strides = (ctypes.c_int64 * 5)(0, sC, sD, sH, sW)
+            _lib.check(L.seunet_forward(plan.handle, _lib.ptr(x2), strides, offs, _lib.ptr(flat), _lib.ptr(ones0),
+                                        _lib.ptr(ones1), _lib.ptr(pred0), _lib.ptr(pred1), st), "seunet_forward")
+            starts = (ctypes.c_int * (3 * b))(*[v for w in wins[i:i + b] for v in w])
+            _lib.check(L.seunet_window_accumulate(_lib.ptr(pred1), starts, b, cube, cube, cube, _lib.ptr(g["acc"]),
+                                                  X, Y, Z, 1, st), "seunet_window_accumulate")
+            i += b
+        _lib.check(L.seunet_window_finalize(_lib.ptr(g["acc"]), _lib.ptr(g["counts"]), X, Y, Z, float(self.threshold),
+                                            _lib.ptr(g["mask"]), 1 if return_prob else 0, st), "seunet_window_finalize")
+        return (g["mask"], g["acc"]) if return_prob else g["mask"]
+
+    def _buffers(self, plan, b, dev):
+        buf = getattr(plan, "_sw_buffers", None)
+        if buf is None:
+            c = self.cube
+            buf = (torch.ones(b, 24, device=dev), torch.ones(b, 12, device=dev),
+                   torch.empty((b, 1, c, c, c), dtype=torch.float32, device=dev),
+                   torch.empty((b, 1, c, c, c), dtype=torch.float32, device=dev))
+            plan._sw_buffers = buf
+        return buf
+
+    @torch.no_grad()
+    def predict(self, img_host, hu_offset=-1024.0):
+        """End-to-end call a user makes: host volume (numpy int16/float32 or CPU tensor, ideally pinned) in, host uint8
+        mask out.  One H2D copy of the stored CT values and one D2H copy of the mask."""
+        t = torch.from_numpy(img_host) if isinstance(img_host, np.ndarray) else img_host
+        dev = next(p for p in self.model._param_tensors()).device
+        d = t.to(dev, non_blocking=True)
+        mask = self.predict_device(d, hu_offset)
+        out = getattr(self, "_host_mask", None)
+        if out is None or out.shape != mask.shape:
+            out = torch.empty(mask.shape, dtype=torch.uint8, pin_memory=True)
+            self._host_mask = out
+        out.copy_(mask, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out
