@@ -82,6 +82,12 @@ int seunet_plan_set_timing(seunet_plan_t* plan, int on);
 int seunet_plan_timing_count(const seunet_plan_t* plan);
 int seunet_plan_timing_get(const seunet_plan_t* plan, int i, const char** label, float* ms, double* flops);
 
+/* Test hook: locate an intermediate tensor inside the bound workspace ("CAT1", "raw:dc5", "T0:1", ...). */
+int seunet_plan_debug_buffer(const seunet_plan_t* plan, const char* name, void** ptr, int* chunks, int* level);
+
+/* Test hook: fill every SM's shared memory with 0xFF so kernels that read stale shared memory are caught. */
+int seunet_debug_poison_smem(seunet_stream_t stream);
+
 /* ---- single-op entry points (parity tests and micro-benchmarks) --------------------------- */
 /* nn.Conv3d(Cin,Cout,k,padding=dil,dilation=dil) forward on chunk-plane activations
  * (SE_UNet.py:15,42,57).  in: [N][in_chunks][D][H][W][8] storage type; w: fp32 (Cout,Cin,k,k,k);

@@ -356,10 +356,13 @@ int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil)
   g->Cin = Cin;
   g->paired = (Cin == 8);
   if (g->paired) {
+    // 9 (kh,kw) taps -> 5 K=16 steps.  The unpaired tap must be tap 0: its dummy second K half (zero weights)
+    // then reads the next voxel, which is still inside the halo tile - a dummy half after the LAST tap would read
+    // past the TMA box, and 0 * (stale shared memory that happens to be Inf/NaN) poisons the accumulator.
     g->KC = 8; g->nchunks = 1; g->nsteps = 5;
     for (int s = 0; s < 5; ++s) {
-      g->psteps[s].tap_a = (int8_t)(2 * s);
-      g->psteps[s].tap_b = (int8_t)(2 * s + 1 < 9 ? 2 * s + 1 : -1);
+      g->psteps[s].tap_a = (int8_t)(s == 0 ? 0 : 2 * s - 1);
+      g->psteps[s].tap_b = (int8_t)(s == 0 ? -1 : 2 * s);
       g->psteps[s].cbase_a = 0; g->psteps[s].cbase_b = 0;
     }
   } else {

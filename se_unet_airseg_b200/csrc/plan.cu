@@ -308,6 +308,31 @@ extern "C" int seunet_plan_timing_get(const seunet_plan_t* p, int i, const char*
   return 0;
 }
 extern "C" size_t seunet_plan_workspace_bytes(const seunet_plan_t* p) { return p ? p->ws_bytes : 0; }
+
+// Test hook: locate an intermediate tensor inside the bound workspace.  Names: the activation buffers
+// "XB","CAT1","DC5IN","D2","P1","CAT2","DC3IN","DC42IN","D1F","P2","CAT3","DC1IN","DC22IN","D0F","P3","CAT4","E7F"
+// (chunk planes), "raw:<layer>" (raw conv output, chunk planes; training-mode plans keep one per layer),
+// "T0:<level>" / "T1:<level>" (fp32 head accumulators, chunks = 0).
+extern "C" int seunet_plan_debug_buffer(const seunet_plan_t* p, const char* name, void** ptr, int* chunks, int* level) {
+  if (!p || !p->ws) { seunet_set_error("debug_buffer: plan not bound"); return 1; }
+  static const char* bnames[B_COUNT] = {"XB", "CAT1", "DC5IN", "D2", "P1", "CAT2", "DC3IN", "DC42IN", "D1F",
+                                        "P2", "CAT3", "DC1IN", "DC22IN", "D0F", "P3", "CAT4", "E7F"};
+  const std::string n(name);
+  for (int b = 0; b < B_COUNT; ++b)
+    if (n == bnames[b]) { *ptr = p->ws + p->buf_off[b]; *chunks = kBufs[b].chunks; *level = kBufs[b].level; return 0; }
+  if (n.rfind("raw:", 0) == 0) {
+    for (int i = 0; i < 18; ++i)
+      if (n.substr(4) == kSse[i].name) { *ptr = p->ws + p->sse_conv[i].raw_off; *chunks = p->sse_conv[i].g.COUT / 8; *level = kSse[i].level; return 0; }
+    for (int i = 0; i < 6; ++i)
+      if (n.substr(4) == kCat[i].name) { *ptr = p->ws + p->cat_conv[i].raw_off; *chunks = p->cat_conv[i].g.COUT / 8; *level = kCat[i].level; return 0; }
+  }
+  if ((n.rfind("T0:", 0) == 0 || n.rfind("T1:", 0) == 0) && n.size() == 4) {
+    const int l = n[3] - '0';
+    if (l >= 0 && l < (n[1] == '0' ? 4 : 3)) { *ptr = p->ws + (n[1] == '0' ? p->T0_off[l] : p->T1_off[l]); *chunks = 0; *level = l; return 0; }
+  }
+  seunet_set_error("debug_buffer: unknown buffer '%s'", name);
+  return 1;
+}
 extern "C" size_t seunet_plan_wimg_bytes(const seunet_plan_t* p) { return p ? p->wimg_bytes : 0; }
 
 extern "C" int seunet_plan_bind(seunet_plan_t* p, void* workspace, void* wimg, seunet_stream_t stream) {
@@ -516,6 +541,25 @@ extern "C" int seunet_from_chunks(const void* src, int src_chunks, int src_off, 
   const long long V = (long long)D * H * W;
   dim3 grid((unsigned)((V + 255) / 256), (C + 7) / 8, N);
   from_chunks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const act_t*)src, src_chunks, src_off, C, V, dst);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// Test hook: fill the shared memory of every SM with 0xFF (NaN in every 16/32-bit float format) so that a kernel
+// relying on stale shared memory (e.g. 0-weight * garbage in a padded UMMA K half) is caught by the parity tests.
+__global__ void poison_smem_kernel(int bytes) {
+  extern __shared__ uint4 sm[];
+  for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) sm[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+  __syncthreads();
+  if (sm[(threadIdx.x * 7) % (bytes / 16)].x == 1u) printf("unreachable\n");
+}
+extern "C" int seunet_debug_poison_smem(seunet_stream_t stream) {
+  const int bytes = 200 * 1024;
+  SEUNET_CUDA_CHECK(cudaFuncSetAttribute(poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  int dev = 0, sms = 0;
+  SEUNET_CUDA_CHECK(cudaGetDevice(&dev));
+  SEUNET_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  poison_smem_kernel<<<sms * 2, 256, bytes, (cudaStream_t)stream>>>(bytes);
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -38,6 +38,7 @@ def _run_conv(L, x, w, ksize, dil, in_chunks=None, in_off=0, transpose_flip=0):
     stats = torch.zeros(N * COUT * 2, dtype=torch.float64, device=dev)
     scratch = torch.empty(L.seunet_conv_scratch_bytes(Cin, Cout, ksize, dil), dtype=torch.uint8, device=dev)
     wd = w.to(dev).contiguous()
+    _lib.check(L.seunet_debug_poison_smem(st), "poison_smem")   # stale shared memory must never reach the accumulators
     _lib.check(L.seunet_conv_fprop(_lib.ptr(xin), in_chunks, in_off, _lib.ptr(wd), N, D, H, W, Cin, Cout, ksize, dil,
                                    _lib.ptr(out), _lib.ptr(stats), _lib.ptr(scratch), transpose_flip, st), "conv_fprop")
     y = torch.empty(N, Cout, D, H, W, dtype=torch.float32, device=dev)
