@@ -78,6 +78,7 @@ template <int COUT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvKArgs a) {
   constexpr int DT = kConvAccCols / COUT;
+  __shared__ float s_run[4][COUT / 16][32];   // per-epilogue-warp running InstanceNorm partial sums
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16-byte aligned: align to 128 by hand
   const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -234,8 +235,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int row = quarter * 32 + lane;
     const int hh = row >> 3, ww = row & 7;
     uint32_t acc = 0, accph = 0;
+    int run_n = -1;
+    auto flush_stats = [&]() {
+      if (run_n < 0) return;
+#pragma unroll
+      for (int cg = 0; cg < COUT / 16; ++cg) {
+        double* sp = a.stats + ((size_t)run_n * COUT + cg * 16 + (lane & 15)) * 2 + (lane >> 4);
+        atomicAdd(sp, (double)s_run[quarter][cg][lane]);
+        s_run[quarter][cg][lane] = 0.f;
+      }
+    };
+#pragma unroll
+    for (int cg = 0; cg < COUT / 16; ++cg) s_run[quarter][cg][lane] = 0.f;
     for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<DT>(a, tile);
+      if (t.n != run_n) { flush_stats(); run_n = t.n; }
       const int h = t.h0 + hh, w = t.w0 + ww;
       const bool inb = (h < a.H) && (w < a.W);
       mbar_wait(tfull_bar(acc), accph);
@@ -271,9 +285,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           }
         }
         const float tot = warp_xreduce32(red, lane);
-        // lane l < 16: sum of channel cg*16+l ; lane l >= 16: sum of squares of channel cg*16+l-16
-        double* sp = a.stats + ((size_t)t.n * COUT + cg * 16 + (lane & 15)) * 2 + (lane >> 4);
-        atomicAdd(sp, (double)tot);
+        // lane l < 16: sum of channel cg*16+l ; lane l >= 16: sum of squares of channel cg*16+l-16.
+        // Totals are kept per warp across the tiles of this persistent CTA and flushed with one fp64 atomic
+        // per (channel, moment) when the sample changes / at the end: same-address atomics serialise in L2.
+        s_run[quarter][cg][lane] += tot;
       }
       tc_fence_before();
       __syncwarp();
@@ -281,6 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       acc ^= 1u;
       if (acc == 0) accph ^= 1u;
     }
+    flush_stats();
   }
 
   tc_fence_before();
@@ -337,7 +353,7 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, act_t* __restrict_
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-static constexpr uint32_t kSmemBudget = 225u * 1024u;
+static constexpr uint32_t kSmemBudget = 222u * 1024u;  // + 2 KB static smem (s_run) + alignment slack <= 227 KB
 static constexpr uint32_t kBarBytes = 8u * 64u;
 
 int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil) {
@@ -499,7 +515,7 @@ template <int COUT>
 static int conv_launch_t(const ConvLaunch& L, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SEUNET_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SEUNET_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr_set = true;
   }
   conv_tc_kernel<COUT><<<L.grid, kConvThreads, L.g.smem_bytes, st>>>(L.tmap, L.a);
