@@ -90,13 +90,16 @@ int seunet_debug_poison_smem(seunet_stream_t stream);
 
 /* ---- single-op entry points (parity tests and micro-benchmarks) --------------------------- */
 /* nn.Conv3d(Cin,Cout,k,padding=dil,dilation=dil) forward on chunk-plane activations
- * (SE_UNet.py:15,42,57).  in: [N][in_chunks][D][H][W][8] storage type; w: fp32 (Cout,Cin,k,k,k);
- * out: raw conv output [N][COUT/8][D][H][W][8]; stats: [N][COUT][2] fp64 (sum, sum sq), zeroed by
- * the call. scratch must hold seunet_conv_scratch_bytes(). COUT = Cout rounded up to 16/32/64. */
+ * (SE_UNet.py:15,42,57).  in: [N][in_chunks][D][H][W][8] 16-bit; w: fp32 (Cout,Cin,k,k,k);
+ * out: conv output [N][ceil(Cout/8)][D][H][W][8]; stats: [N][COUT][2] fp64 (sum, sum sq; COUT = Cout rounded
+ * up to 16/32/64), zeroed by the call, or NULL.  scratch must hold seunet_conv_scratch_bytes().
+ * transpose_flip=1: the data-gradient operator (w is the FORWARD weight (Cin_op, Cout_op, k,k,k), taps mirrored).
+ * bf16=1: operands and output are bf16 (gradient tensors) instead of the activation storage type.
+ * accum_out=1 (bf16 only): out += result (gradient accumulation at fan-out nodes). */
 size_t seunet_conv_scratch_bytes(int Cin, int Cout, int ksize, int dil);
 int seunet_conv_fprop(const void* in, int in_chunks, int in_chunk_off, const float* w, int N, int D, int H, int W,
                       int Cin, int Cout, int ksize, int dil, void* out, double* stats, void* scratch,
-                      int transpose_flip, seunet_stream_t stream);
+                      int transpose_flip, int bf16, int accum_out, seunet_stream_t stream);
 /* fp32 NCDHW <-> chunk-plane storage conversion helpers (tests, sliding-window driver). */
 int seunet_to_chunks(const float* src, int N, int C, int D, int H, int W, void* dst, int dst_chunks, int dst_off,
                      seunet_stream_t stream);

@@ -34,7 +34,7 @@ SIGNATURES = {
     "seunet_plan_debug_buffer": (_i, [_vp, _c.c_char_p, _c.POINTER(_vp), _c.POINTER(_i), _c.POINTER(_i)]),
     "seunet_debug_poison_smem": (_i, [_vp]),
     "seunet_conv_scratch_bytes": (_sz, [_i, _i, _i, _i]),
-    "seunet_conv_fprop": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "seunet_conv_fprop": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "seunet_to_chunks": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "seunet_from_chunks": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "seunet_hu_windows": (_i, [_vp, _i, _i64, _c.c_double, _vp, _vp]),

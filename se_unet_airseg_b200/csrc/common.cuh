@@ -60,6 +60,26 @@ __device__ __forceinline__ Chunk8 floats_to_chunk(const float* f) {
   return c;
 }
 
+// Gradient tensors are always bf16 (range of fp32: no loss scaling needed in the backward pass).
+__device__ __forceinline__ void chunk_to_floats_bf16(const Chunk8& c, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&c.u[i]);
+    float2 v = __bfloat1622float2(t);
+    f[2 * i] = v.x; f[2 * i + 1] = v.y;
+  }
+}
+__device__ __forceinline__ Chunk8 floats_to_chunk_bf16(const float* f) {
+  Chunk8 c;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    c.u[i] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  return c;
+}
+typedef __nv_bfloat16 grad_t;
+
 __device__ __forceinline__ Chunk8 ld_chunk(const void* p) {
   Chunk8 c;
   const uint4 v = *reinterpret_cast<const uint4*>(p);
@@ -161,6 +181,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
 __host__ __device__ __forceinline__ uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// general form: separate A/B formats (0 = f16, 1 = bf16) and majors (0 = K-major, 1 = MN-major)
+__host__ __device__ __forceinline__ uint32_t umma_idesc2(uint32_t fmt_a, uint32_t fmt_b, uint32_t a_mn, uint32_t b_mn,
+                                                         uint32_t M, uint32_t N) {
+  return (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {

@@ -163,9 +163,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // uniform registers; only the tcgen05.mma / tcgen05.commit themselves are issued by one elected lane.
     {
       uint32_t st = 0, ph = 0, wcount = 0, acc = 0, accph = 0, wready = 0;
-      const uint32_t idesc1 = umma_idesc(SEUNET_UMMA_FMT, 128, COUT);
-      const uint32_t idesc2 = umma_idesc(SEUNET_UMMA_FMT, 128, 2 * COUT);
-      const uint32_t idesc3 = umma_idesc(SEUNET_UMMA_FMT, 128, 3 * COUT);
+      const uint32_t idesc1 = umma_idesc(a.fmt, 128, COUT);
+      const uint32_t idesc2 = umma_idesc(a.fmt, 128, 2 * COUT);
+      const uint32_t idesc3 = umma_idesc(a.fmt, 128, 3 * COUT);
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<DT>(a, tile);
         mbar_wait(tempty_bar(acc), accph ^ 1u);
@@ -237,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     uint32_t acc = 0, accph = 0;
     int run_n = -1;
     auto flush_stats = [&]() {
-      if (run_n < 0) return;
+      if (run_n < 0 || a.stats == nullptr) return;
 #pragma unroll
       for (int cg = 0; cg < COUT / 16; ++cg) {
         double* sp = a.stats + ((size_t)run_n * COUT + cg * 16 + (lane & 15)) * 2 + (lane >> 4);
@@ -261,7 +261,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         float red[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) red[i] = 0.f;
-        act_t* obase = a.out +
+        uint16_t* obase = reinterpret_cast<uint16_t*>(a.out) +
             ((size_t)(t.n * a.out_chunks_total + a.out_chunk_off + cg * 2) * a.D) * plane_elems +
             ((size_t)h * a.W + w) * 8;
 #pragma unroll 1
@@ -279,9 +279,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               red[i] += f[i];
               red[16 + i] += f[i] * f[i];
             }
-            act_t* o = obase + (size_t)d * plane_elems;
-            st_chunk(o, floats_to_chunk(f));
-            st_chunk(o + (size_t)a.D * plane_elems, floats_to_chunk(f + 8));
+            uint16_t* o = obase + (size_t)d * plane_elems;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              if (cg * 2 + k >= a.out_real_chunks) break;
+              uint16_t* ok = o + (size_t)k * a.D * plane_elems;
+              if (a.out_bf16) {
+                if (a.accum_out) {
+                  float old[8];
+                  chunk_to_floats_bf16(ld_chunk(ok), old);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[8 * k + i] += old[i];
+                }
+                st_chunk(ok, floats_to_chunk_bf16(f + 8 * k));
+              } else {
+                st_chunk(ok, floats_to_chunk(f + 8 * k));
+              }
+            }
           }
         }
         const float tot = warp_xreduce32(red, lane);
@@ -311,11 +325,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 // weight packing: fp32 (Cout, Cin, k,k,k) -> UMMA image [chunk][step][khalf][nkd*COUT][8]
 // ---------------------------------------------------------------------------------------------
 struct PackArgs {
-  int Cin_real, Cout_real, COUT, ksize, nkd, KC, nchunks, nsteps, transpose_flip;
+  int Cin_real, Cout_real, COUT, ksize, nkd, KC, nchunks, nsteps, transpose_flip, bf16;
   PackStep steps[kConvMaxSteps];
 };
 
-__global__ void conv_pack_kernel(const float* __restrict__ w, act_t* __restrict__ img, const __grid_constant__ PackArgs p) {
+__global__ void conv_pack_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, const __grid_constant__ PackArgs p) {
   const int rows = p.nkd * p.COUT;
   const size_t total = (size_t)p.nchunks * p.nsteps * 2 * rows * 8;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -346,7 +360,8 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, act_t* __restrict_
         }
       }
     }
-    img[i] = f2act(val);
+    if (p.bf16) { __nv_bfloat16 b = __float2bfloat16_rn(val); img[i] = *reinterpret_cast<uint16_t*>(&b); }
+    else { act_t h = f2act(val); img[i] = *reinterpret_cast<uint16_t*>(&h); }
   }
 }
 
@@ -356,8 +371,13 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, act_t* __restrict_
 static constexpr uint32_t kSmemBudget = 222u * 1024u;  // + 2 KB static smem (s_run) + alignment slack <= 227 KB
 static constexpr uint32_t kBarBytes = 8u * 64u;
 
-int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil) {
+int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil, int bf16) {
   memset(g, 0, sizeof(*g));
+#ifdef SEUNET_ACT_BF16
+  g->bf16 = 1;
+#else
+  g->bf16 = bf16 < 0 ? 0 : bf16;
+#endif
   g->Cin_real = Cin_real; g->Cout_real = Cout_real; g->ksize = ksize; g->dil = (ksize == 3) ? dil : 0;
   if (ksize != 1 && ksize != 3) { seunet_set_error("conv: kernel size %d unsupported", ksize); return 1; }
   if (ksize == 3 && dil != 1 && dil != 2) { seunet_set_error("conv: dilation %d unsupported", dil); return 1; }
@@ -421,10 +441,11 @@ int conv_pack_weights(const ConvGeom& g, const float* w_fp32, void* wimg, int tr
   p.Cin_real = g.Cin_real; p.Cout_real = g.Cout_real; p.COUT = g.COUT; p.ksize = g.ksize;
   p.nkd = g.ksize == 3 ? 3 : 1; p.KC = g.KC; p.nchunks = g.nchunks; p.nsteps = g.nsteps;
   p.transpose_flip = transpose_flip;
+  p.bf16 = g.bf16;
   memcpy(p.steps, g.psteps, sizeof(p.steps));
   const size_t total = g.wimg_bytes() / 2;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 1024);
-  conv_pack_kernel<<<blocks, 256, 0, st>>>(w_fp32, (act_t*)wimg, p);
+  conv_pack_kernel<<<blocks, 256, 0, st>>>(w_fp32, (uint16_t*)wimg, p);
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -448,7 +469,7 @@ static PFN_encodeTiled get_encode_fn() {
 int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int W,
                      const void* in, int in_chunks_total, int in_chunk_off,
                      void* out, int out_chunks_total, int out_chunk_off,
-                     double* stats, const void* wimg, int num_sms) {
+                     double* stats, const void* wimg, int num_sms, int accum_out, int out_real_chunks) {
   L->g = g;
   ConvKArgs& a = L->a;
   memset(&a, 0, sizeof(a));
@@ -472,8 +493,12 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
   a.a_sbo = (uint32_t)lineW * 16u;
   a.b_lbo = (uint32_t)nkd * g.COUT * 16u;
   a.wimg = (const uint8_t*)wimg;
-  a.out = (act_t*)out;
+  a.out = out;
   a.stats = stats;
+  a.fmt = g.bf16 ? 1u : 0u;
+  a.out_bf16 = g.bf16;
+  a.accum_out = accum_out;
+  a.out_real_chunks = out_real_chunks < 0 ? g.COUT / 8 : out_real_chunks;
   const uint32_t a_lbo = (uint32_t)HV * 16u;
   for (int s = 0; s < g.nsteps; ++s) {
     const PackStep& ps = g.psteps[s];
@@ -491,7 +516,7 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
     a.b_delta[s] = (uint64_t)(cs.b_off >> 4);
   }
   if (in_chunk_off + g.Cin / 8 > in_chunks_total) { seunet_set_error("conv: input slice exceeds buffer"); return 1; }
-  if (out_chunk_off + g.COUT / 8 > out_chunks_total) { seunet_set_error("conv: output slice exceeds buffer"); return 1; }
+  if (out_chunk_off + a.out_real_chunks > out_chunks_total) { seunet_set_error("conv: output slice exceeds buffer"); return 1; }
 
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) { seunet_set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)"); return 1; }
@@ -499,11 +524,7 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
   cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
   cuuint32_t box[4] = {(cuuint32_t)(8 * lineW), (cuuint32_t)(kConvTileH + 2 * halo), 1u, (cuuint32_t)(g.KC / 8)};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-#ifdef SEUNET_ACT_BF16
-  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-#else
-  const CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-#endif
+  const CUtensorMapDataType dt = g.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = enc(&L->tmap, dt, 4, const_cast<void*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { seunet_set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return 1; }

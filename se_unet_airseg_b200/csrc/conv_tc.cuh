@@ -29,8 +29,12 @@ struct ConvKArgs {
   int nstages, wslots, nsteps;
   uint32_t stage_bytes, box_bytes, wchunk_bytes;
   uint32_t a_sbo, b_lbo;
+  uint32_t fmt;          // UMMA operand format of activations AND weights: 0 = f16, 1 = bf16
+  int out_bf16;          // epilogue writes bf16 (gradients) instead of the activation storage type
+  int accum_out;         // epilogue adds to the existing output (gradient accumulation of fan-out nodes)
+  int out_real_chunks;   // only the first out_real_chunks 8-channel planes are written (COUT padding)
   const uint8_t* wimg;   // packed weights: [chunk][step][khalf][nkd*COUT rows][8]
-  act_t* out;            // raw conv output, chunk-plane layout
+  void* out;             // conv output, chunk-plane layout (16-bit elements)
   double* stats;         // [N][COUT][2] running (sum, sum of squares), fp64 atomics
   ConvStep steps[kConvMaxSteps];
   uint64_t a_delta[kConvMaxSteps];   // per-step additive delta of the A smem descriptor (addr | lbo<<16)
@@ -50,13 +54,14 @@ struct ConvGeom {
   int dil;                  // conv dilation (3x3x3 only)
   int KC, nchunks, nsteps, wslots, nstages;
   bool paired;              // Cin == 8: two taps share one K=16 step
+  int bf16;                 // operands (activations + packed weights) are bf16 (gradient operators)
   uint32_t stage_bytes, box_bytes, wchunk_bytes, smem_bytes;
   PackStep psteps[kConvMaxSteps];
   size_t wimg_bytes() const { return (size_t)nchunks * wchunk_bytes; }
 };
 
 // Fill geometry for a layer. Returns 0 on success.
-int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil);
+int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil, int bf16 = -1 /* -1: storage type */);
 
 // Pack fp32 weights (Cout_real, Cin_real, k, k, k) into the UMMA image.  transpose_flip=1 builds
 // the data-gradient operator (roles of Cin/Cout swapped, taps mirrored).
@@ -74,5 +79,5 @@ struct ConvLaunch {
 int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int W,
                      const void* in, int in_chunks_total, int in_chunk_off,
                      void* out, int out_chunks_total, int out_chunk_off,
-                     double* stats, const void* wimg, int num_sms);
+                     double* stats, const void* wimg, int num_sms, int accum_out = 0, int out_real_chunks = -1);
 int conv_launch_run(const ConvLaunch& L, cudaStream_t st);

@@ -571,16 +571,18 @@ extern "C" size_t seunet_conv_scratch_bytes(int Cin, int Cout, int ksize, int di
 }
 extern "C" int seunet_conv_fprop(const void* in, int in_chunks, int in_chunk_off, const float* w, int N, int D, int H,
                                  int W, int Cin, int Cout, int ksize, int dil, void* out, double* stats, void* scratch,
-                                 int transpose_flip, seunet_stream_t stream) {
+                                 int transpose_flip, int bf16, int accum_out, seunet_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   ConvGeom g;
-  if (conv_geom_init(&g, Cin, Cout, ksize, dil)) return 1;
+  if (conv_geom_init(&g, Cin, Cout, ksize, dil, bf16)) return 1;
   int dev = 0, sms = 0;
   SEUNET_CUDA_CHECK(cudaGetDevice(&dev));
   SEUNET_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (conv_pack_weights(g, w, scratch, transpose_flip, st)) return 1;
-  SEUNET_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * N * g.COUT * 2, st));
+  if (stats) SEUNET_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * N * g.COUT * 2, st));
   ConvLaunch L;
-  if (conv_launch_init(&L, g, N, D, H, W, in, in_chunks, in_chunk_off, out, g.COUT / 8, 0, stats, scratch, sms)) return 1;
+  if (conv_launch_init(&L, g, N, D, H, W, in, in_chunks, in_chunk_off, out, (Cout + 7) / 8, 0, stats, scratch, sms, accum_out,
+                       (Cout + 7) / 8))
+    return 1;
   return conv_launch_run(L, st);
 }

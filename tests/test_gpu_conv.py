@@ -18,7 +18,23 @@ def _store_dtype(L):
     return torch.float16 if L.seunet_act_dtype() == 0 else torch.bfloat16
 
 
-def _run_conv(L, x, w, ksize, dil, in_chunks=None, in_off=0, transpose_flip=0):
+def to_chunk_planes(x, chunks, off, dtype):
+    """(N,C,D,H,W) fp32 -> chunk planes [N][chunks][D][H][W][8] of `dtype` with x occupying planes [off, off+ceil(C/8))."""
+    N, C, D, H, W = x.shape
+    k = (C + 7) // 8
+    buf = torch.zeros(N, chunks, D, H, W, 8, dtype=dtype, device=x.device)
+    xp = torch.zeros(N, k * 8, D, H, W, dtype=x.dtype, device=x.device)
+    xp[:, :C] = x
+    buf[:, off:off + k] = xp.view(N, k, 8, D, H, W).permute(0, 1, 3, 4, 5, 2).to(dtype)
+    return buf
+
+
+def from_chunk_planes(buf, C):
+    N, k, D, H, W, _ = buf.shape
+    return buf.permute(0, 1, 5, 2, 3, 4).reshape(N, k * 8, D, H, W)[:, :C].float()
+
+
+def _run_conv(L, x, w, ksize, dil, in_chunks=None, in_off=0, transpose_flip=0, bf16=0, accum_into=None):
     from se_unet_airseg_b200 import _lib
     N, Cin, D, H, W = x.shape
     Cout = w.shape[1] if transpose_flip else w.shape[0]
@@ -26,25 +42,25 @@ def _run_conv(L, x, w, ksize, dil, in_chunks=None, in_off=0, transpose_flip=0):
     assert cin_k == Cin
     dev = torch.device("cuda", 0)
     COUT = 16 if Cout <= 16 else (32 if Cout <= 32 else 64)
+    sdt = torch.bfloat16 if bf16 else _store_dtype(L)
     if in_chunks is None:
-        in_chunks = (max(Cin, 8) + 7) // 8
-        if ksize == 1 or Cin > 8:
-            in_chunks = ((Cin + 15) // 16) * 2
-    xin = torch.zeros(N * in_chunks * D * H * W * 8, dtype=_store_dtype(L), device=dev)
-    xd = x.to(dev).contiguous()
+        in_chunks = 1 if (Cin <= 8 and ksize == 3) else ((Cin + 15) // 16) * 2
     st = _lib.stream_ptr()
-    _lib.check(L.seunet_to_chunks(_lib.ptr(xd), N, Cin, D, H, W, _lib.ptr(xin), in_chunks, in_off, st), "to_chunks")
-    out = torch.zeros(N * (COUT // 8) * D * H * W * 8, dtype=_store_dtype(L), device=dev)
+    xin = to_chunk_planes(x.to(dev), in_chunks, in_off, sdt)
+    oc = (Cout + 7) // 8
+    if accum_into is not None:
+        out = to_chunk_planes(accum_into.to(dev), oc, 0, sdt)
+    else:
+        out = torch.full((N, oc, D, H, W, 8), float("nan"), dtype=sdt, device=dev)
     stats = torch.zeros(N * COUT * 2, dtype=torch.float64, device=dev)
     scratch = torch.empty(L.seunet_conv_scratch_bytes(Cin, Cout, ksize, dil), dtype=torch.uint8, device=dev)
     wd = w.to(dev).contiguous()
     _lib.check(L.seunet_debug_poison_smem(st), "poison_smem")   # stale shared memory must never reach the accumulators
     _lib.check(L.seunet_conv_fprop(_lib.ptr(xin), in_chunks, in_off, _lib.ptr(wd), N, D, H, W, Cin, Cout, ksize, dil,
-                                   _lib.ptr(out), _lib.ptr(stats), _lib.ptr(scratch), transpose_flip, st), "conv_fprop")
-    y = torch.empty(N, Cout, D, H, W, dtype=torch.float32, device=dev)
-    _lib.check(L.seunet_from_chunks(_lib.ptr(out), COUT // 8, 0, N, Cout, D, H, W, _lib.ptr(y), st), "from_chunks")
+                                   _lib.ptr(out), _lib.ptr(stats), _lib.ptr(scratch), transpose_flip, bf16,
+                                   1 if accum_into is not None else 0, st), "conv_fprop")
     torch.cuda.synchronize()
-    return y.cpu(), stats.cpu().view(N, COUT, 2)
+    return from_chunk_planes(out, Cout).cpu(), stats.cpu().view(N, COUT, 2)
 
 
 CASES = [
@@ -104,6 +120,20 @@ def test_conv_reads_channel_slice_of_concat_buffer(cuda_lib):
     w = torch.randn(32, 16, 3, 3, 3, generator=g) / 20.0
     ref = F.conv3d(x.to(sdt).double(), w.to(sdt).double(), padding=1).float()
     y, _ = _run_conv(L, x, w, 3, 1, in_chunks=8, in_off=5)
+    assert (y - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item() * 1.5
+
+
+def test_conv_bf16_dgrad_accumulates_into_output(cuda_lib):
+    """Backward use: bf16 gradient operands, transposed/mirrored weights, out += result; 40 output channels exercise the
+    channel-plane mask (COUT padded to 64, only 5 planes written)."""
+    L = cuda_lib
+    g = torch.Generator().manual_seed(8)
+    w = torch.randn(32, 40, 3, 3, 3, generator=g) / 30.0          # forward conv 40 -> 32
+    dy = torch.randn(2, 32, 8, 16, 8, generator=g)
+    base = torch.randn(2, 40, 8, 16, 8, generator=g)
+    bq = lambda t: t.to(torch.bfloat16).double()
+    ref = (bq(base) + F.conv_transpose3d(bq(dy), bq(w), padding=1)).float()
+    y, _ = _run_conv(L, dy, w, 3, 1, transpose_flip=1, bf16=1, accum_into=base)
     assert (y - ref).abs().max().item() <= 2.0 ** -8 * ref.abs().max().item() * 1.5
 
 
