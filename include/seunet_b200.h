@@ -100,6 +100,14 @@ size_t seunet_conv_scratch_bytes(int Cin, int Cout, int ksize, int dil);
 int seunet_conv_fprop(const void* in, int in_chunks, int in_chunk_off, const float* w, int N, int D, int H, int W,
                       int Cin, int Cout, int ksize, int dil, void* out, double* stats, void* scratch,
                       int transpose_flip, int bf16, int accum_out, seunet_stream_t stream);
+/* Weight gradient of the same conv (autograd of SE_UNet.py:15/42/57): dw[co][ci][k][k][k] = sum x * dy.
+ * x: activations (storage type) [N][x_chunks][D][H][W][8], slice of Cin channels at x_chunk_off;
+ * dy: SAME storage type (tcgen05 kind::f16 needs equal operand formats) [N][dy_chunks][D][H][W][8] with at least
+ * COUT/8 planes from dy_chunk_off; dw: fp32, overwritten. */
+size_t seunet_wgrad_scratch_bytes(int Cin, int Cout, int ksize);
+int seunet_conv_wgrad(const void* x, int x_chunks, int x_chunk_off, const void* dy, int dy_chunks, int dy_chunk_off,
+                      int N, int D, int H, int W, int Cin, int Cout, int ksize, int dil, void* scratch, float* dw,
+                      seunet_stream_t stream);
 /* fp32 NCDHW <-> chunk-plane storage conversion helpers (tests, sliding-window driver). */
 int seunet_to_chunks(const float* src, int N, int C, int D, int H, int W, void* dst, int dst_chunks, int dst_off,
                      seunet_stream_t stream);

@@ -35,6 +35,8 @@ SIGNATURES = {
     "seunet_debug_poison_smem": (_i, [_vp]),
     "seunet_conv_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "seunet_conv_fprop": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "seunet_wgrad_scratch_bytes": (_sz, [_i, _i, _i]),
+    "seunet_conv_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "seunet_to_chunks": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "seunet_from_chunks": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "seunet_hu_windows": (_i, [_vp, _i, _i64, _c.c_double, _vp, _vp]),

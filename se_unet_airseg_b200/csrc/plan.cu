@@ -3,6 +3,7 @@
 #include "../../include/seunet_b200.h"
 #include "conv_tc.cuh"
 #include "pointwise.cuh"
+#include "wgrad_tc.cuh"
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -585,4 +586,22 @@ extern "C" int seunet_conv_fprop(const void* in, int in_chunks, int in_chunk_off
                        (Cout + 7) / 8))
     return 1;
   return conv_launch_run(L, st);
+}
+
+extern "C" size_t seunet_wgrad_scratch_bytes(int Cin, int Cout, int ksize) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  return wgrad_partial_bytes(Cin, Cout, ksize, sms);
+}
+extern "C" int seunet_conv_wgrad(const void* x, int x_chunks, int x_chunk_off, const void* dy, int dy_chunks, int dy_chunk_off,
+                                 int N, int D, int H, int W, int Cin, int Cout, int ksize, int dil, void* scratch, float* dw,
+                                 seunet_stream_t stream) {
+  int dev = 0, sms = 0;
+  SEUNET_CUDA_CHECK(cudaGetDevice(&dev));
+  SEUNET_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  WgradLaunch L;
+  if (wgrad_launch_init(&L, N, D, H, W, Cin, Cout, ksize, dil, x, x_chunks, x_chunk_off, 0, dy, dy_chunks, dy_chunk_off,
+                        (float*)scratch, sms))
+    return 1;
+  return wgrad_launch_run(L, dw, nullptr, (cudaStream_t)stream);
 }

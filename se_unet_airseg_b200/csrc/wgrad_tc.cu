@@ -1,0 +1,283 @@
+// tcgen05 weight-gradient kernel: dW[co][ci][tap] = sum_{n,voxel} X[n,ci,voxel+shift(tap)] * DY[n,co,voxel]
+// (autograd of the nn.Conv3d call sites SE_UNet.py:15/42/57, reached from loss.backward(), train.py:246/439/602).
+//
+// GEMM view per tap: D[ci, co] += A[ci, k] * B[co, k] with k = voxels.  Both operands are "MN-major" in UMMA terms and
+// the chunk-plane activation layout [C/8][h][w][8] IS the no-swizzle MN-major canonical layout
+// ((8,1,m),(8,k)):((1,8,SBO),(8,LBO)): 8 channels contiguous (16 B), 8 consecutive w voxels 16 B apart form a core
+// matrix, the next 8 voxels (next h line) are LBO away, the next 8 channels (next chunk plane) SBO away.  So, exactly
+// as in the forward kernel, one TMA box per input plane feeds all kw taps by start-address offsets.
+//   * UMMA M = 128 input channels (16 chunk planes; planes beyond Cin read junk whose rows are never used),
+//     N = Cout (16/32/64), K = 16 voxels (two h lines of the 16x8 tile) -> 8 MMAs per (tile plane, tap).
+//   * A pass fixes (kd, kh) - 9 passes for 3x3x3 - and keeps the three kw accumulators [128 x 3*Cout] in TMEM for
+//     the whole kernel: the accumulation over ALL voxels of the CTA's tile planes happens inside TMEM (fp32).
+//     1x1x1 convs use one pass per block of 128 input channels.
+//   * grid = npass * ctas_per_pass persistent CTAs; each writes its partial [taps][128][Cout] once; a small
+//     reduction kernel sums the partials in a fixed order (deterministic) into the flat fp32 gradient.
+//   * both operands use the activation storage type (tcgen05 kind::f16 faults on mixed f16 x bf16 operands, measured);
+//     dY is therefore stored in that type too, pre-scaled by a per-layer power of two (backward.cu) that the
+//     reduction kernel divides out again.
+#include "wgrad_tc.cuh"
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+
+constexpr int kWgThreads = 192;
+
+template <int COUT>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                const __grid_constant__ WgradKArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t x_addr = smem_base;
+  const uint32_t dy_addr = smem_base + a.nstages * a.x_stage_bytes;
+  const uint32_t bar_addr = smem_base + a.bar_off;
+  auto full_bar = [&](int i) { return bar_addr + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_addr + 8u * (8 + i); };
+  const uint32_t done_bar = bar_addr + 8u * 16;
+  const uint32_t tmem_slot_addr = bar_addr + 8u * 17;
+  const uint32_t count_addr = bar_addr + 8u * 18;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.nstages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot_addr, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot_addr));
+
+  const int pass = blockIdx.x / a.ctas_per_pass;
+  const int rank = blockIdx.x % a.ctas_per_pass;
+  // 3x3x3: pass = kd*3 + kh; 1x1x1: pass = block of 128 input channels
+  const int kd = a.ksize == 3 ? pass / 3 : 1;
+  const int kh = a.ksize == 3 ? pass % 3 : 1;
+  const int ntap = a.ksize == 3 ? 3 : 1;
+  const int x_chunk = a.x_chunk_off + (a.ksize == 3 ? 0 : pass * 16);
+  const int dshift = (kd - 1) * a.dil, hshift = (kh - 1) * a.dil;
+
+  auto decode = [&](int tp, int& n, int& p, int& h0, int& w0) {
+    w0 = (tp % a.tilesW) * 8; tp /= a.tilesW;
+    h0 = (tp % a.tilesH) * 16; tp /= a.tilesH;
+    p = tp % a.D; n = tp / a.D;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      for (int tp = rank; tp < a.numTilePlanes; tp += a.ctas_per_pass) {
+        int n, p, h0, w0;
+        decode(tp, n, p, h0, w0);
+        const int q = p + dshift;
+        if (q < 0 || q >= a.D) continue;
+        mbar_wait(empty_bar(st), ph ^ 1u);
+        mbar_expect_tx(full_bar(st), a.x_box_bytes + a.dy_box_bytes);
+        tma_load_4d(x_addr + st * a.x_stage_bytes, &tmap_x, full_bar(st), 8 * (w0 - a.dil), h0 + hshift, q,
+                    n * a.x_chunks_total + x_chunk);
+        tma_load_4d(dy_addr + st * a.dy_stage_bytes, &tmap_dy, full_bar(st), 8 * w0, h0, p, n * a.dy_chunks_total + a.dy_chunk_off);
+        if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    uint32_t st = 0, ph = 0, any = 0;
+    const uint32_t idesc = umma_idesc2(a.fmt_a, a.fmt_b, 1u, 1u, 128, COUT);
+    const uint32_t line_bytes = (uint32_t)a.lineW * 16u;
+    for (int tp = rank; tp < a.numTilePlanes; tp += a.ctas_per_pass) {
+      int n, p, h0, w0;
+      decode(tp, n, p, h0, w0);
+      const int q = p + dshift;
+      if (q < 0 || q >= a.D) continue;
+      mbar_wait(full_bar(st), ph);
+      tc_fence_after();
+      // A: MN-major, m-groups (chunk planes) SBO = plane pitch, k-groups (h lines) LBO = line pitch
+      const uint64_t abase = umma_desc(x_addr + st * a.x_stage_bytes, line_bytes, a.x_plane_bytes);
+      // B: MN-major, n-groups (chunk planes of dY) SBO = 128 voxels * 16 B, k-groups (h lines) LBO = 8 voxels * 16 B
+      const uint64_t bbase = umma_desc(dy_addr + st * a.dy_stage_bytes, 128u, 2048u);
+      for (int kw = 0; kw < ntap; ++kw) {
+        const uint32_t a_tap = (uint32_t)(kw * a.dil) * 16u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint64_t adesc = abase + (uint64_t)((a_tap + 2u * j * line_bytes) >> 4);
+          const uint64_t bdesc = bbase + (uint64_t)((2u * j * 128u) >> 4);
+          if (elect_one_sync()) umma_f16(tmem_base + kw * COUT, adesc, bdesc, idesc, (any | (uint32_t)j) != 0u ? 1u : 0u);
+        }
+      }
+      any = 1;
+      if (elect_one_sync()) umma_commit(empty_bar(st));
+      __syncwarp();
+      if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
+    }
+    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(count_addr), "r"(any) : "memory");
+    __syncwarp();
+    if (elect_one_sync()) umma_commit(done_bar);
+    __syncwarp();
+  } else {
+    // epilogue: after ALL MMAs of this CTA, dump [ntap][128][COUT] fp32 to the partial buffer
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    uint32_t any;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(any) : "r"(count_addr));
+    float* dst = a.partial + ((size_t)blockIdx.x * ntap * 128 + row) * COUT;
+    for (int kw = 0; kw < ntap; ++kw) {
+#pragma unroll 1
+      for (int cg = 0; cg < COUT / 16; ++cg) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + kw * COUT + cg * 16, v);
+        tmem_ld_wait();
+        float4* o = reinterpret_cast<float4*>(dst + (size_t)kw * 128 * COUT + cg * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 f;
+          f.x = any ? __uint_as_float(v[4 * i]) : 0.f; f.y = any ? __uint_as_float(v[4 * i + 1]) : 0.f;
+          f.z = any ? __uint_as_float(v[4 * i + 2]) : 0.f; f.w = any ? __uint_as_float(v[4 * i + 3]) : 0.f;
+          o[i] = f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// dW[co][ci][kd][kh][kw] = sum_r partial[pass(kd,kh) or ci-block][r][kw][ci][co]   (fixed summation order)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cin, int Cout, int COUT,
+                                    int ksize, int ctas_per_pass, const float* __restrict__ inv_scale) {
+  const float mul = inv_scale ? inv_scale[0] : 1.f;
+  const int K3 = ksize * ksize * ksize;
+  const int total = Cout * Cin * K3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % K3, ci = (i / K3) % Cin, co = i / (K3 * Cin);
+    int pass, kw, row;
+    if (ksize == 3) { pass = tap / 3; kw = tap % 3; row = ci; }
+    else { pass = ci / 128; kw = 0; row = ci % 128; }
+    const int ntap = ksize == 3 ? 3 : 1;
+    float s = 0.f;
+    for (int r = 0; r < ctas_per_pass; ++r)
+      s += partial[(((size_t)(pass * ctas_per_pass + r) * ntap + kw) * 128 + row) * COUT + co];
+    dw[i] = s * mul;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled wg_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (PFN_encodeTiled)p;
+  return fn;
+}
+
+size_t wgrad_partial_bytes(int Cin, int Cout, int ksize, int num_sms) {
+  WgradLaunch L;
+  if (wgrad_launch_init(&L, 1, 16, 16, 8, Cin, Cout, ksize, 1, nullptr, (Cin + 7) / 8, 0, 0, nullptr, 8, 0, nullptr, num_sms, true))
+    return 0;
+  return (size_t)L.grid * (ksize == 3 ? 3 : 1) * 128 * L.COUT * sizeof(float);
+}
+
+int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int Cout, int ksize, int dil,
+                      const void* x, int x_chunks_total, int x_chunk_off, int x_bf16,
+                      const void* dy, int dy_chunks_total, int dy_chunk_off, float* partial, int num_sms, bool geometry_only) {
+  memset(L, 0, sizeof(*L));
+  WgradKArgs& a = L->a;
+  L->Cin = Cin; L->Cout = Cout; L->ksize = ksize;
+  L->COUT = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : 64);
+  if (Cout > 64 || (ksize != 1 && ksize != 3)) { seunet_set_error("wgrad: unsupported shape"); return 1; }
+  if (ksize == 3 && Cin > 128) { seunet_set_error("wgrad: 3x3x3 with Cin > 128 unsupported"); return 1; }
+  const int halo = ksize == 3 ? dil : 0;
+  const int npass = ksize == 3 ? 9 : (Cin + 127) / 128;
+  a.N = N; a.D = D; a.H = H; a.W = W;
+  a.tilesW = (W + 7) / 8; a.tilesH = (H + 15) / 16;
+  a.numTilePlanes = N * D * a.tilesH * a.tilesW;
+  a.dil = halo; a.ksize = ksize;
+  a.lineW = 8 + 2 * halo;
+  a.ctas_per_pass = std::max(1, num_sms / npass);
+  L->grid = npass * a.ctas_per_pass;
+  // planes per X box: the real channel planes of this pass (<= 16)
+  const int cin_planes_total = (Cin + 7) / 8;
+  const int xplanes = std::min(16, cin_planes_total);
+  a.x_chunks_total = x_chunks_total; a.x_chunk_off = x_chunk_off;
+  a.dy_chunks_total = dy_chunks_total; a.dy_chunk_off = dy_chunk_off;
+  a.x_plane_bytes = 16u * a.lineW * 16u;
+  a.x_box_bytes = a.x_plane_bytes * xplanes;
+  a.x_stage_bytes = (a.x_box_bytes + 127u) & ~127u;
+  a.dy_box_bytes = 128u * L->COUT * 2u;
+  a.dy_stage_bytes = a.dy_box_bytes;
+  int nst = (int)((200u * 1024u) / (a.x_stage_bytes + a.dy_stage_bytes));
+  nst = std::min(nst, 6);
+  if (nst < 2) { seunet_set_error("wgrad: shared memory budget exceeded"); return 1; }
+  a.nstages = nst;
+  uint32_t natural = nst * (a.x_stage_bytes + a.dy_stage_bytes);
+  // junk rows: an M=128 A operand spans 16 chunk planes from the start of the LAST X stage
+  const uint32_t junk_end = (nst - 1) * a.x_stage_bytes + 16u * a.x_plane_bytes + 8u * a.lineW * 16u;
+  natural = std::max(natural, junk_end);
+  a.bar_off = (natural + 127u) & ~127u;
+  L->smem_bytes = a.bar_off + 256u + 128u;
+  if (L->smem_bytes > 224u * 1024u) { seunet_set_error("wgrad: shared memory budget exceeded (%u)", L->smem_bytes); return 1; }
+  a.partial = partial;
+  a.fmt_a = x_bf16 ? 1u : (uint32_t)SEUNET_UMMA_FMT;
+  a.fmt_b = a.fmt_a;  // tcgen05 kind::f16 requires A and B in the SAME format (mixed f16 x bf16 is an illegal instruction)
+  if (geometry_only) return 0;
+  if (ksize == 1 && x_chunk_off + npass * 16 > x_chunks_total + 15) { seunet_set_error("wgrad: bad 1x1 channel blocks"); return 1; }
+  PFN_encodeTiled enc = wg_encode_fn();
+  if (!enc) { seunet_set_error("cuTensorMapEncodeTiled not available"); return 1; }
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)8 * W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N * x_chunks_total};
+    cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+    cuuint32_t box[4] = {(cuuint32_t)(8 * a.lineW), 16u, 1u, (cuuint32_t)xplanes};
+    CUresult r = enc(&L->tmap_x, x_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                     const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seunet_set_error("wgrad: cuTensorMapEncodeTiled(x) failed: %d", (int)r); return 1; }
+  }
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)8 * W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N * dy_chunks_total};
+    cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+    cuuint32_t box[4] = {64u, 16u, 1u, (cuuint32_t)(L->COUT / 8)};
+    CUresult r = enc(&L->tmap_dy, x_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(dy), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { seunet_set_error("wgrad: cuTensorMapEncodeTiled(dy) failed: %d", (int)r); return 1; }
+  }
+  return 0;
+}
+
+template <int COUT>
+static int wgrad_launch_t(const WgradLaunch& L, cudaStream_t st) {
+  SEUNET_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  wgrad_tc_kernel<COUT><<<L.grid, kWgThreads, L.smem_bytes, st>>>(L.tmap_x, L.tmap_dy, L.a);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int wgrad_launch_run(const WgradLaunch& L, float* dw, const float* inv_scale, cudaStream_t st) {
+  int rc;
+  switch (L.COUT) {
+    case 16: rc = wgrad_launch_t<16>(L, st); break;
+    case 32: rc = wgrad_launch_t<32>(L, st); break;
+    case 64: rc = wgrad_launch_t<64>(L, st); break;
+    default: seunet_set_error("wgrad: bad COUT"); return 1;
+  }
+  if (rc) return rc;
+  const int total = L.Cout * L.Cin * L.ksize * L.ksize * L.ksize;
+  wgrad_reduce_kernel<<<std::min((total + 255) / 256, 592), 256, 0, st>>>(L.a.partial, dw, L.Cin, L.Cout, L.COUT, L.ksize,
+                                                                           L.a.ctas_per_pass, inv_scale);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

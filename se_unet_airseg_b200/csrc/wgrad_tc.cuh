@@ -1,0 +1,32 @@
+// tcgen05 weight-gradient launcher (see wgrad_tc.cu).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+struct WgradKArgs {
+  int N, D, H, W;
+  int tilesW, tilesH, numTilePlanes;
+  int dil, ksize, lineW;
+  int ctas_per_pass, nstages;
+  int x_chunks_total, x_chunk_off, dy_chunks_total, dy_chunk_off;
+  uint32_t x_plane_bytes, x_box_bytes, x_stage_bytes, dy_box_bytes, dy_stage_bytes, bar_off;
+  uint32_t fmt_a, fmt_b;
+  float* partial;
+};
+
+struct WgradLaunch {
+  CUtensorMap tmap_x, tmap_dy;
+  WgradKArgs a;
+  int grid, Cin, Cout, COUT, ksize;
+  uint32_t smem_bytes;
+};
+
+size_t wgrad_partial_bytes(int Cin, int Cout, int ksize, int num_sms);
+// x: activations [N][x_chunks_total][D][H][W][8] (slice at x_chunk_off, Cin channels), dy: same 16-bit type [N][dy_chunks_total][..][8]
+int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int Cout, int ksize, int dil,
+                      const void* x, int x_chunks_total, int x_chunk_off, int x_bf16,
+                      const void* dy, int dy_chunks_total, int dy_chunk_off, float* partial, int num_sms,
+                      bool geometry_only = false);
+// runs the kernel and reduces the partials into dw (fp32, (Cout, Cin, k, k, k) layout, overwritten)
+// inv_scale: optional DEVICE scalar multiplied into dw (undoes the power-of-two pre-scaling of dY)
+int wgrad_launch_run(const WgradLaunch& L, float* dw, const float* inv_scale, cudaStream_t st);
