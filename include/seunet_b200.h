@@ -74,6 +74,15 @@ int seunet_forward(seunet_plan_t* plan, const float* x, const int64_t* x_strides
                    const float* params, const float* drop0, const float* drop1, float* pred0, float* pred1,
                    seunet_stream_t stream);
 
+/* Backward of SE_UNet.forward (autograd reached from loss.backward(), train.py:246/300/439/490/602) for a mode-1 plan
+ * whose last seunet_forward used the same x / params / drop factors.  dpred0/dpred1: fp32 gradients w.r.t. the two
+ * logit tensors [batch][1][D][H][W]; grads: flat fp32 gradient buffer in the parameter layout (overwritten).
+ * conv1.bias gradients are exactly 0 (bias cancels in the non-affine InstanceNorm); dc62 (dead code, SE_UNet.py:230)
+ * gets 0 here and None in the host module. */
+int seunet_backward(seunet_plan_t* plan, const float* x, const int64_t* x_strides, const int64_t* x_offsets,
+                    const float* params, const float* drop0, const float* drop1, const float* dpred0,
+                    const float* dpred1, float* grads, seunet_stream_t stream);
+
 /* Optional per-launch timing with CUDA events recorded on the caller's stream (bench roofline).
  * After a forward and a stream synchronize: interval i covers the launches named by `label`
  * ("conv:dc5", "apply:dc5", "cat:ec33", "up:d1", "head", "prep"); flops = algorithmic FLOPs of a
@@ -94,12 +103,13 @@ int seunet_debug_poison_smem(seunet_stream_t stream);
  * out: conv output [N][ceil(Cout/8)][D][H][W][8]; stats: [N][COUT][2] fp64 (sum, sum sq; COUT = Cout rounded
  * up to 16/32/64), zeroed by the call, or NULL.  scratch must hold seunet_conv_scratch_bytes().
  * transpose_flip=1: the data-gradient operator (w is the FORWARD weight (Cin_op, Cout_op, k,k,k), taps mirrored).
- * bf16=1: operands and output are bf16 (gradient tensors) instead of the activation storage type.
- * accum_out=1 (bf16 only): out += result (gradient accumulation at fan-out nodes). */
+ * bf16=1: operands (and storage-format output) are bf16 instead of the build's activation storage type.
+ * grad_out=1: the output is written in the gradient format (fp32 chunk planes [N][ceil(Cout/8)][D][H][W][8]);
+ * accum_out=1 (grad_out only): out += result (gradient accumulation at fan-out nodes). */
 size_t seunet_conv_scratch_bytes(int Cin, int Cout, int ksize, int dil);
 int seunet_conv_fprop(const void* in, int in_chunks, int in_chunk_off, const float* w, int N, int D, int H, int W,
                       int Cin, int Cout, int ksize, int dil, void* out, double* stats, void* scratch,
-                      int transpose_flip, int bf16, int accum_out, seunet_stream_t stream);
+                      int transpose_flip, int bf16, int grad_out, int accum_out, seunet_stream_t stream);
 /* Weight gradient of the same conv (autograd of SE_UNet.py:15/42/57): dw[co][ci][k][k][k] = sum x * dy.
  * x: activations (storage type) [N][x_chunks][D][H][W][8], slice of Cin channels at x_chunk_off;
  * dy: SAME storage type (tcgen05 kind::f16 needs equal operand formats) [N][dy_chunks][D][H][W][8] with at least

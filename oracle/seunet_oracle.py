@@ -102,10 +102,72 @@ def _up(x, factor):
     return F.interpolate(x, scale_factor=factor, mode="trilinear", align_corners=True)
 
 
+class _RoundSTE(torch.autograd.Function):
+    """Round to a 16-bit storage type in the forward, identity in the backward (straight-through)."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        return x.to(dtype).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+# Optional emulation of the CUDA path's 16-bit STORAGE points (conv operands and raw conv outputs) inside the fp32
+# oracle.  Used only by the backward parity tests: LeakyReLU's derivative is discontinuous, so the gradient of ANY
+# 16-bit-storage forward differs from the fp32 gradient by several percent (a fraction ~1e-3 of the activations sits
+# within rounding distance of the kink); the backward kernels are therefore checked against autograd of the oracle
+# evaluated at the same (rounded) forward state.  None = plain fp32 reference semantics.
+EMULATE_STORAGE = None
+
+# "Same forward state" injection (backward parity tests only).  INJECT maps
+#   "in:<layer>"    -> the conv input actually consumed by the CUDA path (its stored 16-bit activations, as fp32)
+#   "w:<layer>"     -> the conv weight as rounded to the storage type
+#   "raw:<layer>"   -> the CUDA path's stored raw conv output
+#   "stats:<layer>" -> (mean, rstd) tensors of shape (N, C, 1, 1, 1) the CUDA path normalised with
+# Each value replaces the oracle's own forward value while gradients flow through the oracle's graph unchanged
+# (v_used = v_oracle + (v_injected - v_oracle).detach()).  The oracle's backward is then the exact fp32 gradient of the
+# network linearised at the CUDA path's forward state, which is what the backward kernels must reproduce: against the
+# plain fp32 forward, LeakyReLU's discontinuous derivative makes ANY 16-bit-storage implementation differ by several
+# percent (a ~1e-3 fraction of activations sits within rounding distance of the kink).
+INJECT = None
+
+
+def _inj(key, t):
+    if INJECT is None or key not in INJECT:
+        return t
+    return t + (INJECT[key].to(t.dtype) - t).detach()
+
+
+def _q(t):
+    return t if EMULATE_STORAGE is None else _RoundSTE.apply(t, EMULATE_STORAGE)
+
+
+def _conv1(name, x, w, b, **kw):
+    if INJECT is not None:
+        return _inj("raw:" + name, F.conv3d(_inj("in:" + name, x), _inj("w:" + name, w), None, **kw))
+    if EMULATE_STORAGE is None:
+        return F.conv3d(x, w, b, **kw)
+    return _q(F.conv3d(_q(x), _q(w), None, **kw))   # the bias cancels in the following InstanceNorm
+
+
+def _inorm_named(name, y):
+    if INJECT is None or ("stats:" + name) not in INJECT:
+        return _inorm(y)
+    mean = y.mean(dim=(2, 3, 4), keepdim=True)
+    var = y.var(dim=(2, 3, 4), unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + 1e-5)
+    m_inj, r_inj = INJECT["stats:" + name]
+    mean = mean + (m_inj.to(y.dtype) - mean).detach()
+    rstd = rstd + (r_inj.to(y.dtype) - rstd).detach()
+    return (y - mean) * rstd
+
+
 def sse_block(sd, name, x, dil, up, gates):
     """SSEConv.forward (SE_UNet.py:24-35) / SSEConv2.forward (SE_UNet.py:68-82)."""
-    e0 = F.conv3d(x, sd[f"{name}.conv1.weight"], sd[f"{name}.conv1.bias"], padding=dil, dilation=dil)
-    e0 = _lrelu(_inorm(e0))
+    e0 = _conv1(name, x, sd[f"{name}.conv1.weight"], sd[f"{name}.conv1.bias"], padding=dil, dilation=dil)
+    e0 = _lrelu(_inorm_named(name, e0))
     e0 = e0 * torch.sigmoid(F.conv3d(e0, sd[f"{name}.conv_se.weight"]))
     if gates == 2:
         e0 = e0 * torch.sigmoid(F.conv3d(e0, sd[f"{name}.conv_se2.weight"]))
@@ -115,7 +177,9 @@ def sse_block(sd, name, x, dil, up, gates):
 
 def cat_block(sd, name, x):
     """CATConv.forward (SE_UNet.py:45-49)."""
-    return _lrelu(_inorm(F.conv3d(x, sd[f"{name}.conv1.weight"])))
+    if x.shape[1] <= 8:       # x33/x63/x93 injection branches stay fp32 in the CUDA path
+        return _lrelu(_inorm(F.conv3d(x, sd[f"{name}.conv1.weight"])))
+    return _lrelu(_inorm_named(name, _conv1(name, x, sd[f"{name}.conv1.weight"], None)))
 
 
 def drop_scale(batch, channel_num, threshold=0.3, generator=None):

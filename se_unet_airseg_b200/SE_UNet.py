@@ -121,6 +121,7 @@ class _Plan:
         self.wimg = torch.empty(L.seunet_plan_wimg_bytes(h), dtype=torch.uint8, device=device)
         _lib.check(L.seunet_plan_bind(h, _lib.ptr(self.ws), _lib.ptr(self.wimg), _lib.stream_ptr()), "seunet_plan_bind")
         self.packed_for = None  # (flat data_ptr, version) the weight image was packed from
+        self.generation = 0     # bumped by every autograd forward (guards backward against workspace reuse)
 
     def pack(self, flat):
         tag = (flat.data_ptr(), flat._version)
@@ -141,7 +142,8 @@ _MAX_PLANS = 4
 
 
 class _SEUNetFunction(torch.autograd.Function):
-    """autograd boundary: forward = seunet_forward, backward = seunet_backward (C ABI)."""
+    """autograd boundary: forward = seunet_forward, backward = seunet_backward (C ABI).  The plan's workspace holds the
+    activations between the two calls, so a second forward on the same plan invalidates a pending backward."""
 
     @staticmethod
     def forward(ctx, module, plan, x, flat, drop0, drop1, *params):
@@ -152,38 +154,37 @@ class _SEUNetFunction(torch.autograd.Function):
         strides = (ctypes.c_int64 * 5)(*x.stride())
         _lib.check(L.seunet_forward(plan.handle, _lib.ptr(x), strides, None, _lib.ptr(flat), _lib.ptr(drop0),
                                     _lib.ptr(drop1), _lib.ptr(pred0), _lib.ptr(pred1), _lib.stream_ptr()), "seunet_forward")
-        ctx.module, ctx.plan = module, plan
+        plan.generation += 1
+        ctx.module, ctx.plan, ctx.generation = module, plan, plan.generation
         ctx.save_for_backward(x, flat, drop0, drop1)
         ctx.shapes = [p.shape for p in params]
-        ctx.mark_non_differentiable()
+        ctx.needs = [p.requires_grad for p in params]
         return pred0, pred1
 
     @staticmethod
     def backward(ctx, g0, g1):
         L = _lib.lib()
-        if not hasattr(L, "seunet_backward"):
-            raise _lib.SeunetError("seunet_backward is not available in this build of libseunet_b200.so")
         x, flat, drop0, drop1 = ctx.saved_tensors
         plan = ctx.plan
-        if plan.mode_tag != ctx.module._fwd_tag.get(id(plan)):
-            raise _lib.SeunetError("backward called after another forward reused the same plan workspace")
-        g0 = torch.zeros_like(flat[:0]) if g0 is None else g0.contiguous()
-        g1 = g1.contiguous() if g1 is not None else None
+        if plan.generation != ctx.generation:
+            raise _lib.SeunetError("backward() after a newer forward pass reused this plan's activation workspace; "
+                                   "call backward before the next forward of the same shape")
+        shape = (x.shape[0], ctx.module.n_classes) + tuple(x.shape[2:])
+        g0 = torch.zeros(shape, dtype=torch.float32, device=x.device) if g0 is None else g0.contiguous().float()
+        g1 = torch.zeros(shape, dtype=torch.float32, device=x.device) if g1 is None else g1.contiguous().float()
         gflat = torch.empty_like(flat)
         strides = (ctypes.c_int64 * 5)(*x.stride())
-        _lib.check(L.seunet_backward(plan.handle, _lib.ptr(x), strides, _lib.ptr(flat), _lib.ptr(drop0), _lib.ptr(drop1),
-                                     _lib.ptr(g0) if g0.numel() else None, _lib.ptr(g1), _lib.ptr(gflat),
-                                     None, _lib.stream_ptr()), "seunet_backward")
+        with torch.cuda.device(x.device):
+            _lib.check(L.seunet_backward(plan.handle, _lib.ptr(x), strides, None, _lib.ptr(flat), _lib.ptr(drop0),
+                                         _lib.ptr(drop1), _lib.ptr(g0), _lib.ptr(g1), _lib.ptr(gflat), _lib.stream_ptr()),
+                       "seunet_backward")
         grads, off = [], 0
-        for shp in ctx.shapes:
-            n = 1
-            for s in shp:
-                n *= s
-            grads.append(gflat[off:off + n].view(shp))
+        for shp, need in zip(ctx.shapes, ctx.needs):
+            n = shp.numel()
+            grads.append(gflat[off:off + n].view(shp) if need else None)
             off += n
-        # dc62 is dead code in the reference graph (SE_UNet.py:230): its gradient is None there too
-        dead = ctx.module._dead_param_index
-        grads[dead] = None
+        # dc62 is dead code in the reference graph (SE_UNet.py:230): its .grad stays None there too
+        grads[ctx.module._dead_param_index] = None
         return (None, None, None, None, None, None, *grads)
 
 

@@ -28,13 +28,14 @@ SIGNATURES = {
     "seunet_plan_bind": (_i, [_vp, _vp, _vp, _vp]),
     "seunet_pack_weights": (_i, [_vp, _vp, _vp]),
     "seunet_forward": (_i, [_vp, _vp, _c.POINTER(_i64), _c.POINTER(_i64), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "seunet_backward": (_i, [_vp, _vp, _c.POINTER(_i64), _c.POINTER(_i64), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "seunet_plan_set_timing": (_i, [_vp, _i]),
     "seunet_plan_timing_count": (_i, [_vp]),
     "seunet_plan_timing_get": (_i, [_vp, _i, _c.POINTER(_c.c_char_p), _c.POINTER(_c.c_float), _c.POINTER(_c.c_double)]),
     "seunet_plan_debug_buffer": (_i, [_vp, _c.c_char_p, _c.POINTER(_vp), _c.POINTER(_i), _c.POINTER(_i)]),
     "seunet_debug_poison_smem": (_i, [_vp]),
     "seunet_conv_scratch_bytes": (_sz, [_i, _i, _i, _i]),
-    "seunet_conv_fprop": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "seunet_conv_fprop": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "seunet_wgrad_scratch_bytes": (_sz, [_i, _i, _i]),
     "seunet_conv_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "seunet_to_chunks": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),

@@ -1,0 +1,621 @@
+// HBM-bound backward kernels: fused sSE-gate / LeakyReLU / InstanceNorm backward (two passes around the
+// per-(n,c) reductions), CAT-block backward with max-pool routing and the analytic injection branch,
+// adjoint trilinear up-sampling, head adjoint and the small-parameter gradient assembly.
+#include "backward.cuh"
+#include <algorithm>
+#include <cstring>
+
+constexpr float kInEps = 1e-5f;
+
+__device__ __forceinline__ float lrelu_grad(float n) { return n > 0.f ? 1.f : 0.01f; }
+__device__ __forceinline__ void atomic_max_pos(unsigned int* p, float v) { atomicMax(p, __float_as_uint(v)); }
+
+// =============================================================================================
+// SSE block backward, pass A
+// =============================================================================================
+template <int C, int GATES>
+__global__ void __launch_bounds__(256) sse_bwd_a_kernel(const __grid_constant__ SseBwdArgs a) {
+  constexpr int LPV = C / 8;     // lanes cooperating on one voxel (one 8-channel chunk each)
+  constexpr int VPW = 32 / LPV;  // voxels per warp
+  __shared__ float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
+  __shared__ float s_red[8][5][C];
+  __shared__ float s_cst[8], s_max[8];
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double s = a.stats[((size_t)n * a.stats_c + c) * 2], q = a.stats[((size_t)n * a.stats_c + c) * 2 + 1];
+    const double mean = s / (double)a.V;
+    double var = q / (double)a.V - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[c] = (float)mean;
+    s_rstd[c] = (float)(1.0 / sqrt(var + (double)kInEps));
+    s_wse[c] = a.wse[c];
+    s_wse2[c] = GATES == 2 ? a.wse2[c] : 0.f;
+    s_weff[c] = a.weff[(size_t)n * 64 + c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = lane % LPV, vsub = lane / LPV;
+  float S1[8], S2[8], Wse[8], Wse2[8], Weff[8], cst = 0.f, mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) S1[i] = S2[i] = Wse[i] = Wse2[i] = Weff[i] = 0.f;
+  auto vreduce = [&](float v) {   // sum over the LPV lanes of one voxel
+#pragma unroll
+    for (int o = 1; o < LPV; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  for (long long vb = ((long long)blockIdx.x * 8 + warp) * VPW; vb < a.V; vb += (long long)gridDim.x * 8 * VPW) {
+    const long long v = vb + vsub;   // V is a multiple of 32, so the whole warp is in range
+    float f[8], nn[8], av[8], e0[8];
+    chunk_to_floats(ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8), f);
+    float p1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = k * 8 + i;
+      nn[i] = (f[i] - s_mean[c]) * s_rstd[c];
+      av[i] = lrelu_(nn[i]);
+      p1 = fmaf(s_wse[c], av[i], p1);
+    }
+    const float g1 = sigmoidf_(vreduce(p1));
+    float a1[8], g2 = 1.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a1[i] = av[i] * g1;
+    if (GATES == 2) {
+      float p2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p2 = fmaf(s_wse2[k * 8 + i], a1[i], p2);
+      g2 = sigmoidf_(vreduce(p2));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e0[i] = a1[i] * g2;
+    const float dT = a.dT[(size_t)n * a.V + v];
+    float de0[8];
+    if (a.dE0) ld_grad8(a.dE0 + (((size_t)n * a.dE0_chunks + a.dE0_off + k) * a.V + v) * 8, de0);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) de0[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) de0[i] = fmaf(s_weff[k * 8 + i], dT, de0[i]);
+    float da1[8], k2 = 0.f;
+    if (GATES == 2) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s2 = fmaf(de0[i], a1[i], s2);
+      k2 = vreduce(s2) * g2 * (1.f - g2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) da1[i] = fmaf(s_wse2[k * 8 + i], k2, de0[i] * g2);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) da1[i] = de0[i];
+    }
+    float s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s1 = fmaf(da1[i], av[i], s1);
+    const float k1 = vreduce(s1) * g1 * (1.f - g1);
+    float dn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = k * 8 + i;
+      const float da = fmaf(s_wse[c], k1, da1[i] * g1);
+      dn[i] = da * lrelu_grad(nn[i]);
+      S1[i] += dn[i];
+      S2[i] = fmaf(dn[i], nn[i], S2[i]);
+      Wse[i] = fmaf(k1, av[i], Wse[i]);
+      Wse2[i] = fmaf(k2, a1[i], Wse2[i]);
+      Weff[i] = fmaf(dT, e0[i], Weff[i]);
+      mx = fmaxf(mx, fabsf(dn[i] * s_rstd[c]));
+    }
+    if (k == 0) cst += dT;
+    st_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
+  }
+  // reduce over the voxel sub-lanes of the warp, then over warps, then one atomic per value per block
+  auto wreduce = [&](float v) {
+#pragma unroll
+    for (int o = LPV; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float r0 = wreduce(S1[i]), r1 = wreduce(S2[i]), r2 = wreduce(Wse[i]), r3 = wreduce(Wse2[i]), r4 = wreduce(Weff[i]);
+    if (vsub == 0) {
+      s_red[warp][0][k * 8 + i] = r0; s_red[warp][1][k * 8 + i] = r1; s_red[warp][2][k * 8 + i] = r2;
+      s_red[warp][3][k * 8 + i] = r3; s_red[warp][4][k * 8 + i] = r4;
+    }
+  }
+  cst = warp_sum(cst);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) { s_cst[warp] = cst; s_max[warp] = mx; }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 5 * C; t += blockDim.x) {
+    const int q = t / C, c = t % C;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += s_red[w][q][c];
+    if (q < 2) atomicAdd(a.redS + ((size_t)n * 64 + c) * 2 + q, (double)s);
+    else if (q == 2) atomicAdd(a.dwse + c, s);
+    else if (q == 3) { if (GATES == 2) atomicAdd(a.dwse2 + c, s); }
+    else atomicAdd(a.dweff + (size_t)n * 64 + c, s);
+  }
+  if (threadIdx.x == 0) {
+    float s = 0.f, m = 0.f;
+    for (int w = 0; w < 8; ++w) { s += s_cst[w]; m = fmaxf(m, s_max[w]); }
+    atomicAdd(a.dcst + n, s);
+    atomic_max_pos(a.dymax, m);
+  }
+}
+
+template <int C>
+static int launch_sse_bwd_a_c(const SseBwdArgs& a, cudaStream_t st) {
+  constexpr int VPB = 8 * (32 / (C / 8));
+  const long long need = (a.V + VPB - 1) / VPB;
+  dim3 grid((unsigned)std::min<long long>(need, 148 * 8), a.N);
+  if (a.wse2) sse_bwd_a_kernel<C, 2><<<grid, 256, 0, st>>>(a);
+  else sse_bwd_a_kernel<C, 1><<<grid, 256, 0, st>>>(a);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_sse_bwd_a(int C, const SseBwdArgs& a, cudaStream_t st) {
+  switch (C) {
+    case 8: return launch_sse_bwd_a_c<8>(a, st);
+    case 16: return launch_sse_bwd_a_c<16>(a, st);
+    case 32: return launch_sse_bwd_a_c<32>(a, st);
+    case 64: return launch_sse_bwd_a_c<64>(a, st);
+  }
+  seunet_set_error("sse_bwd_a: C=%d unsupported", C);
+  return 1;
+}
+
+// =============================================================================================
+// InstanceNorm backward, pass B (shared by SSE and CAT blocks)
+// =============================================================================================
+__device__ __forceinline__ float dy_scale_from_max(unsigned int bits) {
+  const float mx = __uint_as_float(bits);
+  if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
+  float e = 8.f - ceilf(log2f(mx));          // largest |dn*rstd| lands in [2^7, 2^8]
+  e = fminf(fmaxf(e, -100.f), 100.f);
+  return exp2f(e);
+}
+
+__global__ void __launch_bounds__(256) norm_bwd_b_kernel(const __grid_constant__ NormBwdArgs a) {
+  __shared__ float s_mean[8], s_rstd[8], s_m1[8], s_m2[8];
+  __shared__ float s_scale;
+  const int n = blockIdx.z, k = blockIdx.y;
+  if (threadIdx.x < 8) {
+    const int c = k * 8 + threadIdx.x;
+    const double s = a.stats[((size_t)n * a.stats_c + c) * 2], q = a.stats[((size_t)n * a.stats_c + c) * 2 + 1];
+    const double mean = s / (double)a.V;
+    double var = q / (double)a.V - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)kInEps));
+    s_m1[threadIdx.x] = (float)(a.redS[((size_t)n * 64 + c) * 2] / (double)a.V);
+    s_m2[threadIdx.x] = (float)(a.redS[((size_t)n * 64 + c) * 2 + 1] / (double)a.V);
+  }
+  if (threadIdx.x == 8) {
+    const float sc = dy_scale_from_max(*a.dymax);
+    s_scale = sc;
+    if (blockIdx.x == 0 && k == 0 && n == 0) { a.scale_out[0] = sc; a.scale_out[1] = 1.f / sc; }
+  }
+  __syncthreads();
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= a.V) return;
+  float f[8], dn[8], dy[8];
+  chunk_to_floats(ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8), f);
+  ld_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
+  const float sc = s_scale;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float nn = (f[i] - s_mean[i]) * s_rstd[i];
+    float t = s_rstd[i] * (dn[i] - s_m1[i] - nn * s_m2[i]) * sc;
+    dy[i] = fminf(fmaxf(t, -60000.f), 60000.f);
+  }
+  st_chunk(a.dy + (((size_t)n * a.dy_chunks + k) * a.V + v) * 8, floats_to_chunk(dy));
+}
+
+int launch_norm_bwd_b(const NormBwdArgs& a, cudaStream_t st) {
+  dim3 grid((unsigned)((a.V + 255) / 256), a.C / 8, a.N);
+  norm_bwd_b_kernel<<<grid, 256, 0, st>>>(a);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// CAT block backward, pass A:  out = lrelu(IN(y)) [+ lrelu(IN(Wx x))], optional 2x2x2 max-pool fan-out
+// =============================================================================================
+struct CatCoef { float mean[8], rstd[8], mx[8], rx[8], w0[8], w1[8]; };
+
+__device__ __forceinline__ void cat_prologue(const act_t*, const double* stats, int stats_c, long long V, int n, int k, bool hasx,
+                                             const float* wx, int in_ch, const double* mom, CatCoef* s) {
+  if (threadIdx.x < 8) {
+    const int c = k * 8 + threadIdx.x;
+    const double su = stats[((size_t)n * stats_c + c) * 2], q = stats[((size_t)n * stats_c + c) * 2 + 1];
+    const double mean = su / (double)V;
+    double var = q / (double)V - mean * mean;
+    if (var < 0) var = 0;
+    s->mean[threadIdx.x] = (float)mean;
+    s->rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)kInEps));
+    if (hasx) {
+      const double* m = mom + (size_t)n * kMomStride;
+      const double mu0 = m[0] / V, mu1 = m[1] / V;
+      const double c00 = m[2] / V - mu0 * mu0, c11 = m[3] / V - mu1 * mu1, c01 = m[4] / V - mu0 * mu1;
+      const double w0 = wx[c * in_ch], w1 = in_ch > 1 ? wx[c * in_ch + 1] : 0.0;
+      double vx = w0 * w0 * c00 + w1 * w1 * c11 + 2.0 * w0 * w1 * c01;
+      if (vx < 0) vx = 0;
+      s->mx[threadIdx.x] = (float)(w0 * mu0 + w1 * mu1);
+      s->rx[threadIdx.x] = (float)(1.0 / sqrt(vx + (double)kInEps));
+      s->w0[threadIdx.x] = (float)w0;
+      s->w1[threadIdx.x] = (float)w1;
+    }
+  }
+}
+
+template <bool HASX, bool POOL>
+__global__ void __launch_bounds__(256) cat_bwd_a_kernel(const __grid_constant__ CatBwdArgs a) {
+  __shared__ CatCoef s;
+  __shared__ float s_red[8][32];
+  __shared__ float s_max[8];
+  const int n = blockIdx.z, k = blockIdx.y;
+  const long long V = dims_vox(a.d);
+  cat_prologue(a.raw, a.stats, a.stats_c, V, n, k, HASX, a.wx, a.in_ch, a.mom, &s);
+  __syncthreads();
+  const act_t* rawp = a.raw + ((size_t)n * a.raw_chunks + k) * V * 8;
+  const grad_t* gp_ = a.g + ((size_t)n * a.g_chunks + a.g_off + k) * V * 8;
+  grad_t* dnp = a.dn + ((size_t)n * a.dn_chunks + k) * V * 8;
+  float red[32];   // [0..7] S1, [8..15] S2, [16..23] Sx1, [24..31] Sx2
+#pragma unroll
+  for (int i = 0; i < 32; ++i) red[i] = 0.f;
+  float mxv = 0.f;
+  auto xvals = [&](int dz, int hy, int wx, float& x0, float& x1) {
+    x0 = 0.f; x1 = 0.f;
+    if (HASX) {
+      const float* xp = a.x + (a.xo.use ? a.xo.off[n] : n * a.xs[0]) + dz * a.xs[2] + hy * a.xs[3] + wx * a.xs[4];
+      x0 = xp[0];
+      if (a.in_ch > 1) x1 = xp[a.xs[1]];
+    }
+  };
+  // gradient bookkeeping of one voxel given its total output gradient G[8]
+  auto accumulate = [&](long long v, const float* ny, const float* nx, const float* G) {
+    float dn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dn[i] = G[i] * lrelu_grad(ny[i]);
+      red[i] += dn[i];
+      red[8 + i] = fmaf(dn[i], ny[i], red[8 + i]);
+      mxv = fmaxf(mxv, fabsf(dn[i] * s.rstd[i]));
+      if (HASX) {
+        const float dx = G[i] * lrelu_grad(nx[i]);
+        red[16 + i] += dx;
+        red[24 + i] = fmaf(dx, nx[i], red[24 + i]);
+      }
+    }
+    st_grad8(dnp + (size_t)v * 8, dn);
+  };
+  auto norms = [&](long long v, int dz, int hy, int wx, float* ny, float* nx) {
+    float f[8];
+    chunk_to_floats(ld_chunk(rawp + (size_t)v * 8), f);
+    float x0, x1;
+    xvals(dz, hy, wx, x0, x1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ny[i] = (f[i] - s.mean[i]) * s.rstd[i];
+      nx[i] = HASX ? (fmaf(s.w0[i], x0, s.w1[i] * x1) - s.mx[i]) * s.rx[i] : 0.f;
+    }
+  };
+  if (!POOL) {
+    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+      const int wx = (int)(v % a.d.W), hy = (int)((v / a.d.W) % a.d.H), dz = (int)(v / ((long long)a.d.W * a.d.H));
+      float ny[8], nx[8], G[8];
+      norms(v, dz, hy, wx, ny, nx);
+      ld_grad8(gp_ + (size_t)v * 8, G);
+      accumulate(v, ny, nx, G);
+    }
+  } else {
+    const int Dp = a.d.D >> 1, Hp = a.d.H >> 1, Wp = a.d.W >> 1;
+    const long long Vp = (long long)Dp * Hp * Wp;
+    const grad_t* gpool = a.gp + ((size_t)n * a.gp_chunks + a.gp_off + k) * Vp * 8;
+    for (long long pv = blockIdx.x * (long long)blockDim.x + threadIdx.x; pv < Vp; pv += (long long)gridDim.x * blockDim.x) {
+      const int pw = (int)(pv % Wp), ph = (int)((pv / Wp) % Hp), pd = (int)(pv / ((long long)Wp * Hp));
+      // pass 1: arg-max of the forward output per channel (first maximum in (d,h,w) scan order, like max_pool3d)
+      float best[8];
+      int arg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; arg[i] = 0; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int dz = pd * 2 + (j >> 2), hy = ph * 2 + ((j >> 1) & 1), wx = pw * 2 + (j & 1);
+        const long long v = ((long long)dz * a.d.H + hy) * a.d.W + wx;
+        float ny[8], nx[8];
+        norms(v, dz, hy, wx, ny, nx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float o = lrelu_(ny[i]) + (HASX ? lrelu_(nx[i]) : 0.f);
+          if (o > best[i]) { best[i] = o; arg[i] = j; }
+        }
+      }
+      float GP[8];
+      ld_grad8(gpool + (size_t)pv * 8, GP);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int dz = pd * 2 + (j >> 2), hy = ph * 2 + ((j >> 1) & 1), wx = pw * 2 + (j & 1);
+        const long long v = ((long long)dz * a.d.H + hy) * a.d.W + wx;
+        float ny[8], nx[8], G[8];
+        norms(v, dz, hy, wx, ny, nx);
+        ld_grad8(gp_ + (size_t)v * 8, G);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) G[i] += (arg[i] == j) ? GP[i] : 0.f;
+        accumulate(v, ny, nx, G);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float tot = warp_xreduce32(red, lane);
+  s_red[warp][lane] = tot;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mxv = fmaxf(mxv, __shfl_xor_sync(0xffffffffu, mxv, o));
+  if (lane == 0) s_max[warp] = mxv;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += s_red[w][threadIdx.x];
+    const int q = threadIdx.x >> 3, i = threadIdx.x & 7, c = k * 8 + i;
+    if (q < 2) atomicAdd(a.redS + ((size_t)n * 64 + c) * 2 + q, (double)sum);
+    else if (HASX) atomicAdd(a.redSx + ((size_t)n * 64 + c) * 2 + (q - 2), (double)sum);
+  }
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int w = 0; w < 8; ++w) m = fmaxf(m, s_max[w]);
+    atomic_max_pos(a.dymax, m);
+  }
+}
+
+int launch_cat_bwd_a(const CatBwdArgs& a, cudaStream_t st) {
+  const long long V = dims_vox(a.d);
+  const bool pool = a.gp != nullptr, hasx = a.x != nullptr;
+  const long long items = pool ? V / 8 : V;
+  dim3 grid((unsigned)std::min<long long>((items + 255) / 256, 148 * 4), a.C / 8, a.d.N);
+  if (hasx && pool) cat_bwd_a_kernel<true, true><<<grid, 256, 0, st>>>(a);
+  else if (hasx) cat_bwd_a_kernel<true, false><<<grid, 256, 0, st>>>(a);
+  else if (pool) cat_bwd_a_kernel<false, true><<<grid, 256, 0, st>>>(a);
+  else cat_bwd_a_kernel<false, false><<<grid, 256, 0, st>>>(a);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// x-branch weight gradient (x33/x63/x93.conv1.weight): du = rx * (dnx - mean(dnx) - nx * mean(dnx*nx)), dWx = sum du x^T
+__global__ void __launch_bounds__(256) cat_bwd_x_kernel(const __grid_constant__ CatBwdXArgs a) {
+  __shared__ CatCoef s;
+  __shared__ float s_m1[8], s_m2[8];
+  __shared__ float s_red[8][32];
+  const int n = blockIdx.z, k = blockIdx.y;
+  const long long V = dims_vox(a.d);
+  cat_prologue(a.raw, a.stats, a.stats_c, V, n, k, true, a.wx, a.in_ch, a.mom, &s);
+  if (threadIdx.x >= 32 && threadIdx.x < 40) {
+    const int i = threadIdx.x - 32, c = k * 8 + i;
+    s_m1[i] = (float)(a.redSx[((size_t)n * 64 + c) * 2] / (double)V);
+    s_m2[i] = (float)(a.redSx[((size_t)n * 64 + c) * 2 + 1] / (double)V);
+  }
+  __syncthreads();
+  float red[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) red[i] = 0.f;
+  const act_t* rawp = a.raw + ((size_t)n * a.raw_chunks + k) * V * 8;
+  const grad_t* dnp = a.dn + ((size_t)n * a.dn_chunks + k) * V * 8;
+  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
+    const int wx = (int)(v % a.d.W), hy = (int)((v / a.d.W) % a.d.H), dz = (int)(v / ((long long)a.d.W * a.d.H));
+    float f[8], dn[8];
+    chunk_to_floats(ld_chunk_stream(rawp + (size_t)v * 8), f);
+    ld_grad8(dnp + (size_t)v * 8, dn);
+    const float* xp = a.x + (a.xo.use ? a.xo.off[n] : n * a.xs[0]) + dz * a.xs[2] + hy * a.xs[3] + wx * a.xs[4];
+    const float x0 = xp[0], x1 = a.in_ch > 1 ? xp[a.xs[1]] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float ny = (f[i] - s.mean[i]) * s.rstd[i];
+      const float G = dn[i] * (ny > 0.f ? 1.f : 100.f);          // undo the y-branch LeakyReLU derivative
+      const float nx = (fmaf(s.w0[i], x0, s.w1[i] * x1) - s.mx[i]) * s.rx[i];
+      const float dx = G * lrelu_grad(nx);
+      const float du = s.rx[i] * (dx - s_m1[i] - nx * s_m2[i]);
+      red[i] = fmaf(du, x0, red[i]);
+      red[8 + i] = fmaf(du, x1, red[8 + i]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float tot = warp_xreduce32(red, lane);
+  s_red[warp][lane] = tot;
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += s_red[w][threadIdx.x];
+    const int inp = threadIdx.x >> 3, c = k * 8 + (threadIdx.x & 7);
+    if (inp < a.in_ch) atomicAdd(a.dwx + c * a.in_ch + inp, sum);
+  }
+}
+
+int launch_cat_bwd_x(const CatBwdXArgs& a, cudaStream_t st) {
+  const long long V = dims_vox(a.d);
+  dim3 grid((unsigned)std::min<long long>((V + 255) / 256, 148 * 4), a.C / 8, a.d.N);
+  cat_bwd_x_kernel<<<grid, 256, 0, st>>>(a);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// adjoint trilinear interpolation (align_corners=True)
+// =============================================================================================
+struct LerpB { int i0, i1; float l0, l1; };
+__device__ __forceinline__ LerpB lerp_ac_b(int dst, int in_size, int out_size) {
+  const float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
+  const float src = scale * (float)dst;
+  LerpB r;
+  r.i0 = (int)src;
+  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+// weight with which output index o reads source index j along one axis
+__device__ __forceinline__ float axis_weight(int o, int j, int in_size, int out_size) {
+  const LerpB l = lerp_ac_b(o, in_size, out_size);
+  return (l.i0 == j ? l.l0 : 0.f) + (l.i1 == j ? l.l1 : 0.f);
+}
+// candidate output range [lo, hi] whose interpolation may touch source index j
+__device__ __forceinline__ void axis_range(int j, int in_size, int out_size, int& lo, int& hi) {
+  const float inv = in_size > 1 ? (float)(out_size - 1) / (float)(in_size - 1) : 0.f;
+  lo = max(0, (int)floorf((float)(j - 1) * inv) - 1);
+  hi = min(out_size - 1, (int)ceilf((float)(j + 1) * inv) + 1);
+}
+
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(const grad_t* __restrict__ gdst, int gdst_chunks, int gdst_off, Dims sd,
+                                                            grad_t* __restrict__ gsrc, int C8) {
+  const int n = blockIdx.z, k = blockIdx.y;
+  const int Do = sd.D * 2, Ho = sd.H * 2, Wo = sd.W * 2;
+  const long long Vs = dims_vox(sd), Vo = Vs * 8;
+  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (v >= Vs) return;
+  const int jw = (int)(v % sd.W), jh = (int)((v / sd.W) % sd.H), jd = (int)(v / ((long long)sd.W * sd.H));
+  int dlo, dhi, hlo, hhi, wlo, whi;
+  axis_range(jd, sd.D, Do, dlo, dhi);
+  axis_range(jh, sd.H, Ho, hlo, hhi);
+  axis_range(jw, sd.W, Wo, wlo, whi);
+  const grad_t* gp = gdst + ((size_t)n * gdst_chunks + gdst_off + k) * Vo * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int od = dlo; od <= dhi; ++od) {
+    const float wd = axis_weight(od, jd, sd.D, Do);
+    if (wd == 0.f) continue;
+    for (int oh = hlo; oh <= hhi; ++oh) {
+      const float wh = axis_weight(oh, jh, sd.H, Ho) * wd;
+      if (wh == 0.f) continue;
+      for (int ow = wlo; ow <= whi; ++ow) {
+        const float ww = axis_weight(ow, jw, sd.W, Wo) * wh;
+        if (ww == 0.f) continue;
+        float f[8];
+        ld_grad8_cached(gp + (((size_t)od * Ho + oh) * Wo + ow) * 8, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(ww, f[i], acc[i]);
+      }
+    }
+  }
+  st_grad8(gsrc + (((size_t)n * C8 + k) * Vs + v) * 8, acc);
+}
+
+int launch_upsample2_bwd(const grad_t* gdst, int gdst_chunks, int gdst_off, int C, Dims sd, grad_t* gsrc, cudaStream_t st) {
+  const long long Vs = dims_vox(sd);
+  dim3 grid((unsigned)((Vs + 255) / 256), C / 8, sd.N);
+  upsample2_bwd_kernel<<<grid, 256, 0, st>>>(gdst, gdst_chunks, gdst_off, sd, gsrc, C / 8);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// head adjoint for one level: one warp per low-resolution voxel gathers over the (d,h,w) output window
+__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dpred, Dims full, int level, float* __restrict__ dT) {
+  const int n = blockIdx.y;
+  const int Ds = full.D >> level, Hs = full.H >> level, Ws = full.W >> level;
+  const long long Vs = (long long)Ds * Hs * Ws, V = dims_vox(full);
+  const int lane = threadIdx.x & 31;
+  const long long j = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j >= Vs) return;
+  const int jw = (int)(j % Ws), jh = (int)((j / Ws) % Hs), jd = (int)(j / ((long long)Ws * Hs));
+  int dlo, dhi, hlo, hhi, wlo, whi;
+  axis_range(jd, Ds, full.D, dlo, dhi);
+  axis_range(jh, Hs, full.H, hlo, hhi);
+  axis_range(jw, Ws, full.W, wlo, whi);
+  const float* gp = dpred + (size_t)n * V;
+  const int nh = hhi - hlo + 1, nw = whi - wlo + 1;
+  float acc = 0.f;
+  for (int od = dlo; od <= dhi; ++od) {
+    const float wd = axis_weight(od, jd, Ds, full.D);
+    if (wd == 0.f) continue;
+    for (int t = lane; t < nh * nw; t += 32) {
+      const int oh = hlo + t / nw, ow = wlo + t % nw;
+      const float w = wd * axis_weight(oh, jh, Hs, full.H) * axis_weight(ow, jw, Ws, full.W);
+      if (w != 0.f) acc = fmaf(w, __ldg(gp + ((size_t)od * full.H + oh) * full.W + ow), acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) dT[(size_t)n * Vs + j] = acc;
+}
+
+int launch_head_bwd_level(const float* dpred, Dims full, int level, float* dT, cudaStream_t st) {
+  const long long Vs = (long long)(full.D >> level) * (full.H >> level) * (full.W >> level);
+  dim3 grid((unsigned)((Vs + 7) / 8), full.N);
+  head_bwd_kernel<<<grid, 256, 0, st>>>(dpred, full, level, dT);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ src, long long n, float* __restrict__ dst) {
+  double s = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += src[i];
+  __shared__ double sh[8];
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(dst, (float)t);
+  }
+}
+int launch_sum(const float* src, long long n, float* dst, cudaStream_t st) {
+  SEUNET_CUDA_CHECK(cudaMemsetAsync(dst, 0, sizeof(float), st));
+  sum_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 592), 256, 0, st>>>(src, n, dst);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// =============================================================================================
+// small parameters: conv2 (weight, bias), conv_se, conv_se2, dc0_0 / dc0_1 weights
+//   weff[n][c] = sum_j h_j[n] W2[j][c],  cst[n] = sum_j h_j[n] b2[j],  h_j[n] = hw[2k+j] * drop[n][2k+j]
+// =============================================================================================
+__global__ void small_grads_kernel(const float* __restrict__ params, const float* __restrict__ drop0,
+                                   const float* __restrict__ drop1, const __grid_constant__ SmallGradArgs a,
+                                   const float* __restrict__ dweff, const float* __restrict__ dcst,
+                                   const float* __restrict__ dwse, const float* __restrict__ dwse2, float* __restrict__ grads) {
+  const int b = blockIdx.x, c = threadIdx.x, N = a.N;
+  const SmallGradBlock blk = a.blk[b];
+  const int hc = blk.head == 0 ? 24 : 12;
+  const float* drop = blk.head == 0 ? drop0 : drop1;
+  const float* hw = params + a.hw_off[blk.head];
+  __shared__ float s_part[2][64];
+  float dw2[2] = {0.f, 0.f}, dh[2] = {0.f, 0.f};
+  if (c < blk.C) {
+    for (int n = 0; n < N; ++n) {
+      const float g = dweff[((size_t)b * N + n) * 64 + c];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float dr = drop[n * hc + 2 * blk.k + j];
+        dw2[j] = fmaf(hw[2 * blk.k + j] * dr, g, dw2[j]);
+        dh[j] = fmaf(dr * params[blk.w2_off + j * blk.C + c], g, dh[j]);
+      }
+    }
+    grads[blk.w2_off + c] = dw2[0];
+    grads[blk.w2_off + blk.C + c] = dw2[1];
+    grads[blk.wse_off + c] = dwse[b * 64 + c];
+    if (blk.wse2_off >= 0) grads[blk.wse2_off + c] = dwse2[b * 64 + c];
+  }
+  s_part[0][c] = dh[0];
+  s_part[1][c] = dh[1];
+  __syncthreads();
+  if (c < 2) {
+    float s = 0.f;
+    for (int i = 0; i < 64; ++i) s += s_part[c][i];
+    float db2 = 0.f;
+    for (int n = 0; n < N; ++n) {
+      const float dr = drop[n * hc + 2 * blk.k + c], gc = dcst[(size_t)b * N + n];
+      db2 = fmaf(hw[2 * blk.k + c] * dr, gc, db2);
+      s = fmaf(dr * params[blk.b2_off + c], gc, s);
+    }
+    grads[blk.b2_off + c] = db2;
+    grads[a.hw_off[blk.head] + 2 * blk.k + c] = s;
+  }
+}
+
+int launch_small_grads(const float* params, const float* drop0, const float* drop1, const SmallGradArgs& a,
+                       const float* dweff, const float* dcst, const float* dwse, const float* dwse2, float* grads,
+                       cudaStream_t st) {
+  small_grads_kernel<<<18, 64, 0, st>>>(params, drop0, drop1, a, dweff, dcst, dwse, dwse2, grads);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

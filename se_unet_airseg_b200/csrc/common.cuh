@@ -78,7 +78,35 @@ __device__ __forceinline__ Chunk8 floats_to_chunk_bf16(const float* f) {
   }
   return c;
 }
+// Gradients w.r.t. activations (dn scratch and the per-buffer gradient accumulators) are fp32 by default: the weight
+// gradient is a heavily cancelling sum, and bf16 storage of its inputs costs ~10x the 1e-2 tolerance at small volumes.
+// -DSEUNET_GRAD_BF16 halves that traffic at the price of accuracy.
+#ifdef SEUNET_GRAD_BF16
 typedef __nv_bfloat16 grad_t;
+__device__ __forceinline__ void ld_grad8(const grad_t* p, float* f) { chunk_to_floats_bf16(ld_chunk_stream(p), f); }
+__device__ __forceinline__ void ld_grad8_cached(const grad_t* p, float* f) {
+  Chunk8 c; const uint4 v = *reinterpret_cast<const uint4*>(p); c.u[0] = v.x; c.u[1] = v.y; c.u[2] = v.z; c.u[3] = v.w;
+  chunk_to_floats_bf16(c, f);
+}
+__device__ __forceinline__ void st_grad8(grad_t* p, const float* f) {
+  const Chunk8 c = floats_to_chunk_bf16(f);
+  *reinterpret_cast<uint4*>(p) = make_uint4(c.u[0], c.u[1], c.u[2], c.u[3]);
+}
+#else
+typedef float grad_t;
+__device__ __forceinline__ void ld_grad8(const grad_t* p, float* f) {
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void ld_grad8_cached(const grad_t* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void st_grad8(grad_t* p, const float* f) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+#endif
 
 __device__ __forceinline__ Chunk8 ld_chunk(const void* p) {
   Chunk8 c;

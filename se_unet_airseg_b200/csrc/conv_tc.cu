@@ -236,6 +236,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int hh = row >> 3, ww = row & 7;
     uint32_t acc = 0, accph = 0;
     int run_n = -1;
+    const float oscale = a.out_scale ? __ldg(a.out_scale) : 1.f;
     auto flush_stats = [&]() {
       if (run_n < 0 || a.stats == nullptr) return;
 #pragma unroll
@@ -261,9 +262,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         float red[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) red[i] = 0.f;
-        uint16_t* obase = reinterpret_cast<uint16_t*>(a.out) +
-            ((size_t)(t.n * a.out_chunks_total + a.out_chunk_off + cg * 2) * a.D) * plane_elems +
-            ((size_t)h * a.W + w) * 8;
+        const size_t obase = ((size_t)(t.n * a.out_chunks_total + a.out_chunk_off + cg * 2) * a.D) * plane_elems +
+                             ((size_t)h * a.W + w) * 8;   // element offset
 #pragma unroll 1
         for (int s = 0; s < DT; ++s) {
           const int d = t.d0 + slot_plane<DT>(s, a.dil);
@@ -275,25 +275,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              f[i] = __uint_as_float(v[i]);
+              f[i] = __uint_as_float(v[i]) * oscale;
               red[i] += f[i];
               red[16 + i] += f[i] * f[i];
             }
-            uint16_t* o = obase + (size_t)d * plane_elems;
+            const size_t eo = obase + (size_t)d * plane_elems;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               if (cg * 2 + k >= a.out_real_chunks) break;
-              uint16_t* ok = o + (size_t)k * a.D * plane_elems;
-              if (a.out_bf16) {
+              const size_t ek = eo + (size_t)k * a.D * plane_elems;
+              if (a.out_bf16) {   // gradient-format output (grad_t), optionally accumulating
+                grad_t* ok = reinterpret_cast<grad_t*>(a.out) + ek;
                 if (a.accum_out) {
                   float old[8];
-                  chunk_to_floats_bf16(ld_chunk(ok), old);
+                  ld_grad8_cached(ok, old);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[8 * k + i] += old[i];
                 }
-                st_chunk(ok, floats_to_chunk_bf16(f + 8 * k));
+                st_grad8(ok, f + 8 * k);
               } else {
-                st_chunk(ok, floats_to_chunk(f + 8 * k));
+                st_chunk(reinterpret_cast<uint16_t*>(a.out) + ek, floats_to_chunk(f + 8 * k));
               }
             }
           }
@@ -325,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 // weight packing: fp32 (Cout, Cin, k,k,k) -> UMMA image [chunk][step][khalf][nkd*COUT][8]
 // ---------------------------------------------------------------------------------------------
 struct PackArgs {
-  int Cin_real, Cout_real, COUT, ksize, nkd, KC, nchunks, nsteps, transpose_flip, bf16;
+  int Cin_real, Cout_real, COUT, ksize, nkd, KC, nchunks, nsteps, transpose_flip, bf16, co_off, co_total;
   PackStep steps[kConvMaxSteps];
 };
 
@@ -356,7 +357,7 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, uint16_t* __restri
         // taps mirrored.  Cin_real/Cout_real are given in the gradient operator's own roles.
         if (co < p.Cout_real && ci < p.Cin_real) {
           if (K == 3) { kd = 2 - kd; kh = 2 - kh; kw = 2 - kw; }
-          val = w[((size_t)ci * p.Cout_real + co) * K3 + (kd * K + kh) * K + kw];
+          val = w[((size_t)ci * p.co_total + p.co_off + co) * K3 + (kd * K + kh) * K + kw];
         }
       }
     }
@@ -435,13 +436,16 @@ int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil,
   return 0;
 }
 
-int conv_pack_weights(const ConvGeom& g, const float* w_fp32, void* wimg, int transpose_flip, cudaStream_t st) {
+int conv_pack_weights(const ConvGeom& g, const float* w_fp32, void* wimg, int transpose_flip, cudaStream_t st, int co_off,
+                      int co_total) {
   PackArgs p;
   memset(&p, 0, sizeof(p));
   p.Cin_real = g.Cin_real; p.Cout_real = g.Cout_real; p.COUT = g.COUT; p.ksize = g.ksize;
   p.nkd = g.ksize == 3 ? 3 : 1; p.KC = g.KC; p.nchunks = g.nchunks; p.nsteps = g.nsteps;
   p.transpose_flip = transpose_flip;
   p.bf16 = g.bf16;
+  p.co_off = co_off;
+  p.co_total = co_total < 0 ? g.Cout_real : co_total;
   memcpy(p.steps, g.psteps, sizeof(p.steps));
   const size_t total = g.wimg_bytes() / 2;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 1024);
@@ -469,7 +473,8 @@ static PFN_encodeTiled get_encode_fn() {
 int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int W,
                      const void* in, int in_chunks_total, int in_chunk_off,
                      void* out, int out_chunks_total, int out_chunk_off,
-                     double* stats, const void* wimg, int num_sms, int accum_out, int out_real_chunks) {
+                     double* stats, const void* wimg, int num_sms, int accum_out, int out_real_chunks, int grad_out,
+                     const float* out_scale) {
   L->g = g;
   ConvKArgs& a = L->a;
   memset(&a, 0, sizeof(a));
@@ -496,7 +501,8 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
   a.out = out;
   a.stats = stats;
   a.fmt = g.bf16 ? 1u : 0u;
-  a.out_bf16 = g.bf16;
+  a.out_bf16 = grad_out;
+  a.out_scale = out_scale;
   a.accum_out = accum_out;
   a.out_real_chunks = out_real_chunks < 0 ? g.COUT / 8 : out_real_chunks;
   const uint32_t a_lbo = (uint32_t)HV * 16u;

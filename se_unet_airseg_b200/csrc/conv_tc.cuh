@@ -30,9 +30,10 @@ struct ConvKArgs {
   uint32_t stage_bytes, box_bytes, wchunk_bytes;
   uint32_t a_sbo, b_lbo;
   uint32_t fmt;          // UMMA operand format of activations AND weights: 0 = f16, 1 = bf16
-  int out_bf16;          // epilogue writes bf16 (gradients) instead of the activation storage type
+  int out_bf16;          // epilogue writes the gradient format grad_t (fp32 by default) instead of the storage type
   int accum_out;         // epilogue adds to the existing output (gradient accumulation of fan-out nodes)
   int out_real_chunks;   // only the first out_real_chunks 8-channel planes are written (COUT padding)
+  const float* out_scale; // optional DEVICE scalar multiplied into the result (undoes the dY pre-scaling in dgrad)
   const uint8_t* wimg;   // packed weights: [chunk][step][khalf][nkd*COUT rows][8]
   void* out;             // conv output, chunk-plane layout (16-bit elements)
   double* stats;         // [N][COUT][2] running (sum, sum of squares), fp64 atomics
@@ -65,7 +66,10 @@ int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil,
 
 // Pack fp32 weights (Cout_real, Cin_real, k, k, k) into the UMMA image.  transpose_flip=1 builds
 // the data-gradient operator (roles of Cin/Cout swapped, taps mirrored).
-int conv_pack_weights(const ConvGeom& g, const float* w_fp32, void* wimg, int transpose_flip, cudaStream_t st);
+// co_off/co_total (transpose_flip only): the operator produces output channels [co_off, co_off+Cout_real) of a
+// forward weight tensor with co_total input channels (dgrad of wide layers is split into <= 64-channel pieces).
+int conv_pack_weights(const ConvGeom& g, const float* w_fp32, void* wimg, int transpose_flip, cudaStream_t st,
+                      int co_off = 0, int co_total = -1);
 
 struct ConvLaunch {
   ConvGeom g;
@@ -79,5 +83,6 @@ struct ConvLaunch {
 int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int W,
                      const void* in, int in_chunks_total, int in_chunk_off,
                      void* out, int out_chunks_total, int out_chunk_off,
-                     double* stats, const void* wimg, int num_sms, int accum_out = 0, int out_real_chunks = -1);
+                     double* stats, const void* wimg, int num_sms, int accum_out = 0, int out_real_chunks = -1,
+                     int grad_out = 0 /* 1: output is grad_t */, const float* out_scale = nullptr);
 int conv_launch_run(const ConvLaunch& L, cudaStream_t st);

@@ -4,6 +4,7 @@
 #include "conv_tc.cuh"
 #include "pointwise.cuh"
 #include "wgrad_tc.cuh"
+#include "backward.cuh"
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -147,6 +148,16 @@ struct seunet_plan {
   size_t xp1_off, xp2_off, mom_off, weff_off, wcst_off, stats_off, stats_bytes;
   size_t ws_bytes, wimg_bytes;
   HeadwArgs headw;
+  // ---- backward (training-mode plans only; see plan_bwd.inc)
+  struct DgradPiece { ConvGeom g; ConvLaunch L; size_t wimg_off; int co_off, co_total, out_buf, out_chunk, accum; };
+  std::vector<DgradPiece> sse_dgrad[18], cat_dgrad[6];
+  WgradLaunch sse_wgrad[18], cat_wgrad[6];
+  SmallGradArgs smallg;
+  size_t gbuf_off[B_COUNT];          // bf16 gradients w.r.t. the activation buffers
+  size_t dn_off[4], dy_off[4];       // per-level dn (bf16) / dY (storage type) scratch
+  size_t dT0_off[4], dT1_off[3];     // head-accumulator gradients (level 0 aliases dpred)
+  size_t bwd_red_off, bwd_red_bytes; // zeroed at the start of every backward
+  size_t redS_off, redSx_off, dwse_off, dwse2_off, dweff_off, dcst_off, dymax_off, scale_off, partial_off;
   uint8_t* ws = nullptr;
   uint8_t* wimg = nullptr;
   XOffsets xo;                      // per-sample input offsets of the current forward
@@ -167,6 +178,10 @@ struct seunet_plan {
 };
 
 static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+// backward-pass planning hooks (plan_bwd.inc)
+static int bwd_plan_create(seunet_plan* p, size_t& wimg, size_t& off);
+static int bwd_plan_bind(seunet_plan* p);
+static int bwd_pack_weights(seunet_plan* p, const float* params, cudaStream_t st);
 
 extern "C" int seunet_version(void) { return 1; }
 extern "C" int seunet_act_dtype(void) {
@@ -242,8 +257,6 @@ extern "C" int seunet_plan_create(seunet_plan_t** out, int batch, int D, int H, 
     p->cat_conv[i].wimg_off = wimg;
     wimg += align_up(p->cat_conv[i].g.wimg_bytes());
   }
-  p->wimg_bytes = wimg;
-
   // --- workspace layout
   size_t off = 0;
   for (int b = 0; b < B_COUNT; ++b) {
@@ -275,6 +288,8 @@ extern "C" int seunet_plan_create(seunet_plan_t** out, int batch, int D, int H, 
   p->mom_off = off; off += align_up((size_t)3 * batch * kMomStride * sizeof(double));
   p->weff_off = off; off += align_up((size_t)18 * batch * 64 * 4);
   p->wcst_off = off; off += align_up((size_t)18 * batch * 4);
+  if (mode == 1 && bwd_plan_create(p, wimg, off)) { delete p; return 1; }
+  p->wimg_bytes = wimg;
   p->ws_bytes = off;
 
   // --- folded head weights table
@@ -331,6 +346,22 @@ extern "C" int seunet_plan_debug_buffer(const seunet_plan_t* p, const char* name
     const int l = n[3] - '0';
     if (l >= 0 && l < (n[1] == '0' ? 4 : 3)) { *ptr = p->ws + (n[1] == '0' ? p->T0_off[l] : p->T1_off[l]); *chunks = 0; *level = l; return 0; }
   }
+  if (n.rfind("stats:", 0) == 0) {   // fp64 [N][COUT][2] (sum, sum of squares); *chunks = COUT
+    for (int i = 0; i < 18; ++i)
+      if (n.substr(6) == kSse[i].name) { *ptr = p->ws + p->sse_conv[i].stats_off; *chunks = p->sse_conv[i].g.COUT; *level = kSse[i].level; return 0; }
+    for (int i = 0; i < 6; ++i)
+      if (n.substr(6) == kCat[i].name) { *ptr = p->ws + p->cat_conv[i].stats_off; *chunks = p->cat_conv[i].g.COUT; *level = kCat[i].level; return 0; }
+  }
+  if (p->mode == 1 && (n.rfind("dy:", 0) == 0 || n.rfind("dn:", 0) == 0) && n.size() == 4) {
+    const int l = n[3] - '0';
+    if (l >= 0 && l < 4) { *ptr = p->ws + (n[1] == 'y' ? p->dy_off[l] : p->dn_off[l]); *chunks = l == 0 ? 4 : 8; *level = l; return 0; }
+  }
+  if (p->mode == 1 && n.rfind("scale:", 0) == 0) {
+    *ptr = p->ws + p->scale_off + 8 * atoi(n.c_str() + 6); *chunks = 0; *level = 0; return 0;
+  }
+  if (p->mode == 1 && n.rfind("g:", 0) == 0)
+    for (int b = 1; b < B_COUNT; ++b)
+      if (n.substr(2) == bnames[b]) { *ptr = p->ws + p->gbuf_off[b]; *chunks = kBufs[b].chunks; *level = kBufs[b].level; return 0; }
   seunet_set_error("debug_buffer: unknown buffer '%s'", name);
   return 1;
 }
@@ -365,6 +396,7 @@ extern "C" int seunet_plan_bind(seunet_plan_t* p, void* workspace, void* wimg, s
                          p->num_sms))
       return 1;
   }
+  if (p->mode == 1 && bwd_plan_bind(p)) return 1;
   return 0;
 }
 
@@ -375,6 +407,7 @@ extern "C" int seunet_pack_weights(seunet_plan_t* p, const float* params, seunet
     if (conv_pack_weights(p->sse_conv[i].g, params + p->sse_conv[i].w_off, p->wimg + p->sse_conv[i].wimg_off, 0, st)) return 1;
   for (int i = 0; i < 6; ++i)
     if (conv_pack_weights(p->cat_conv[i].g, params + p->cat_conv[i].w_off, p->wimg + p->cat_conv[i].wimg_off, 0, st)) return 1;
+  if (p->mode == 1 && bwd_pack_weights(p, params, st)) return 1;
   return 0;
 }
 
@@ -572,7 +605,7 @@ extern "C" size_t seunet_conv_scratch_bytes(int Cin, int Cout, int ksize, int di
 }
 extern "C" int seunet_conv_fprop(const void* in, int in_chunks, int in_chunk_off, const float* w, int N, int D, int H,
                                  int W, int Cin, int Cout, int ksize, int dil, void* out, double* stats, void* scratch,
-                                 int transpose_flip, int bf16, int accum_out, seunet_stream_t stream) {
+                                 int transpose_flip, int bf16, int grad_out, int accum_out, seunet_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   ConvGeom g;
   if (conv_geom_init(&g, Cin, Cout, ksize, dil, bf16)) return 1;
@@ -582,8 +615,9 @@ extern "C" int seunet_conv_fprop(const void* in, int in_chunks, int in_chunk_off
   if (conv_pack_weights(g, w, scratch, transpose_flip, st)) return 1;
   if (stats) SEUNET_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * N * g.COUT * 2, st));
   ConvLaunch L;
+  if (accum_out && !grad_out) { seunet_set_error("conv_fprop: accum_out needs grad_out"); return 1; }
   if (conv_launch_init(&L, g, N, D, H, W, in, in_chunks, in_chunk_off, out, (Cout + 7) / 8, 0, stats, scratch, sms, accum_out,
-                       (Cout + 7) / 8))
+                       (Cout + 7) / 8, grad_out))
     return 1;
   return conv_launch_run(L, st);
 }
@@ -605,3 +639,5 @@ extern "C" int seunet_conv_wgrad(const void* x, int x_chunks, int x_chunk_off, c
     return 1;
   return wgrad_launch_run(L, dw, nullptr, (cudaStream_t)stream);
 }
+
+#include "plan_bwd.inc"
