@@ -124,6 +124,26 @@ int seunet_to_chunks(const float* src, int N, int C, int D, int H, int W, void* 
 int seunet_from_chunks(const void* src, int src_chunks, int src_off, int N, int C, int D, int H, int W, float* dst,
                        seunet_stream_t stream);
 
+/* ---- losses and optimizer (train.py:51-76; stage combinations 597-599 / 432-435 / 238-243; AdamW 188/386/569) -------
+ * The losses are ratios of BATCH-GLOBAL sums.  seunet_loss_sums reduces this rank's logits to partial sums
+ *   sums[2 heads (en=pred0, de=pred1)][8] = {sum p t, sum p, sum t, sum w (p+1e-4)^0.7 t, sum w (0.2p+0.8t),
+ *                                            sum w p s^2, sum w (p s + s), 0}          (p = sigmoid(logit), fp64, device)
+ * (data-parallel ranks all-reduce the 16 doubles - the reference evaluates the loss on the gathered batch), and
+ * seunet_loss_grad turns the global sums into the scalar stage loss and d loss / d logit.
+ * stage 1: dice(de)+dice(en); 2: gul(de)+0.5 gul(en); 3: stage 2 + 0.5 (atr(en)+atr(de)).
+ * per_sample (optional): [batch][2 heads][2] = per-sample (A, Bs) GUL sums used for hard-mining names (train.py:249-253). */
+int seunet_loss_sums(int stage, const float* pred_en, const float* pred_de, const float* label, const float* weight,
+                     const float* skel, int batch, int64_t voxels_per_sample, double* sums, double* per_sample,
+                     seunet_stream_t stream);
+int seunet_loss_grad(int stage, const float* pred_en, const float* pred_de, const float* label, const float* weight,
+                     const float* skel, int64_t n, const double* sums, float* dpred_en, float* dpred_de, float* loss_out,
+                     seunet_stream_t stream);
+/* torch.optim.AdamW step (amsgrad=False) over the flat parameter / gradient buffers; grad_scale multiplies the gradient
+ * first; [skip_off, skip_off+skip_len) is left untouched (dc62: grad None in the reference => never updated). */
+int seunet_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int step, float grad_scale, int64_t skip_off,
+                      int64_t skip_len, seunet_stream_t stream);
+
 /* ---- sliding-window inference support (prediction.py:39-49, 69-111) ------- */
 /* two_channel(img + offset): img int16 (dtype 0) or fp32 (dtype 1) of nvox voxels -> out[2][nvox] fp32,
  * HU windows [-1024,1024] and [-1000,500] scaled to [0,1]; evaluated in fp64 like the numpy reference. */

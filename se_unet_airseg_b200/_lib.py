@@ -40,6 +40,10 @@ SIGNATURES = {
     "seunet_conv_wgrad": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "seunet_to_chunks": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "seunet_from_chunks": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "seunet_loss_sums": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
+    "seunet_loss_grad": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "seunet_adamw_step": (_i, [_vp, _vp, _vp, _vp, _i64, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _i,
+                               _c.c_float, _i64, _i64, _vp]),
     "seunet_hu_windows": (_i, [_vp, _i, _i64, _c.c_double, _vp, _vp]),
     "seunet_window_accumulate": (_i, [_vp, _c.POINTER(_i), _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
     "seunet_window_finalize": (_i, [_vp, _vp, _i, _i, _i, _c.c_float, _vp, _i, _vp]),

@@ -1,0 +1,110 @@
+"""Data-parallel training step for SE_UNet on B200: one process per GPU (torch.distributed / NCCL over NVLink), the
+B200-native replacement of the reference's single-process `torch.nn.DataParallel` loop (train.py:428-440, 234-247, 592-603).
+
+Per step and rank:
+  forward (C ABI, training plan)  ->  loss partial sums (fused kernel)  ->  all-reduce of 16 fp64 sums [C4]
+  ->  loss gradient from the GLOBAL sums  ->  backward (C ABI)  ->  all-reduce(SUM) of the flat fp32 gradient [C3]
+  ->  fused AdamW on the flat parameter buffer  ->  re-pack the tensor-core weight image (next forward).
+
+The loss is a ratio of batch-global sums (train.py:51-76 evaluated on the gathered batch), so partial sums - not
+per-rank losses - are exchanged, and gradients are SUMMED, not averaged: N ranks x B/N patches reproduce the single-rank
+step on the concatenated batch.  (DropLayer's normaliser is per local batch in the reference too - SE_UNet.py:94 under
+DataParallel - so train-mode numerics depend on the GPU count there as well.)
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+ADAMW_DEFAULTS = dict(lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)   # torch.optim.AdamW(lr=1e-4), train.py:188
+
+
+def loss_from_sums(stage, sums):
+    """Scalar stage loss from the [2][8] global sums (host-side mirror of seunet_loss_grad, for logging/tests)."""
+    e, d = sums[0], sums[1]
+    dice = lambda s: 1.0 - (2.0 * s[0] + 1.0) / (s[1] + s[2] + 1.0)
+    gul = lambda s: 1.0 - (s[3] + 1.0) / (s[4] + 1.0)
+    atr = lambda s: 1.0 - (s[5] + 1.0) / (s[6] + 1.0)
+    if stage == 1:
+        return dice(d) + dice(e)
+    loss = gul(d) + 0.5 * gul(e)
+    if stage == 3:
+        loss = loss + 0.5 * (atr(e) + atr(d))
+    return loss
+
+
+class DataParallelTrainer:
+    def __init__(self, model, stage=2, **adamw):
+        self.model, self.stage = model, stage
+        self.hp = dict(ADAMW_DEFAULTS, **adamw)
+        self.step_count = 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        params = model._param_tensors()
+        self.device = params[0].device
+        if self.device.type != "cuda":
+            raise _lib.SeunetError("DataParallelTrainer needs the model on a CUDA device")
+        # one flat fp32 master copy; the module's Parameters become views of it so state_dict()/checkpoints stay live
+        with torch.no_grad():
+            self.flat = torch.cat([p.detach().reshape(-1).float() for p in params]).contiguous()
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.data = self.flat[off:off + n].view(p.shape)
+                off += n
+        self.grads = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.sums = torch.zeros(16, dtype=torch.float64, device=self.device)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        L = _lib.lib()
+        ic, nc = model.in_channel, model.n_classes
+        self.skip_off = L.seunet_param_offset(ic, nc, b"dc62.conv1.weight")
+        self.skip_len = 48 * 16
+        self._buf = None
+
+    def _buffers(self, shape):
+        if self._buf is None or self._buf[0] != shape:
+            B, D, H, W = shape
+            mk = lambda: torch.empty((B, 1, D, H, W), dtype=torch.float32, device=self.device)
+            self._buf = (shape, mk(), mk(), mk(), mk(), torch.zeros(B * 4, dtype=torch.float64, device=self.device))
+        return self._buf[1:]
+
+    def step(self, x, label, weight=None, skel=None):
+        """One optimisation step on this rank's shard of the batch; returns the (global) loss as a 1-element device tensor
+        (no host synchronisation).  x: (B, in_ch, D, H, W) fp32 CUDA; label/weight/skel: (B, 1, D, H, W) fp32 CUDA."""
+        L = _lib.lib()
+        m = self.model
+        B, _, D, H, W = x.shape
+        st = _lib.stream_ptr()
+        with torch.cuda.device(self.device), torch.no_grad():
+            plan = m._plan(B, D, H, W, 1, self.device)
+            plan.pack(self.flat)
+            plan.generation += 1
+            drop0 = m.dropout1.scale(B, self.device)
+            drop1 = m.dropout2.scale(B, self.device)
+            pe, pd, ge, gd, per_sample = self._buffers((B, D, H, W))
+            strides = (ctypes.c_int64 * 5)(*x.stride())
+            p_ = _lib.ptr
+            _lib.check(L.seunet_forward(plan.handle, p_(x), strides, None, p_(self.flat), p_(drop0), p_(drop1), p_(pe), p_(pd), st),
+                       "seunet_forward")
+            V = D * H * W
+            _lib.check(L.seunet_loss_sums(self.stage, p_(pe), p_(pd), p_(label), p_(weight), p_(skel), B, V, p_(self.sums),
+                                          p_(per_sample), st), "seunet_loss_sums")
+            if self.world > 1:
+                dist.all_reduce(self.sums, op=dist.ReduceOp.SUM)          # C4: batch-global loss sums
+            _lib.check(L.seunet_loss_grad(self.stage, p_(pe), p_(pd), p_(label), p_(weight), p_(skel), B * V, p_(self.sums),
+                                          p_(ge), p_(gd), p_(self.loss), st), "seunet_loss_grad")
+            _lib.check(L.seunet_backward(plan.handle, p_(x), strides, None, p_(self.flat), p_(drop0), p_(drop1), p_(ge), p_(gd),
+                                         p_(self.grads), st), "seunet_backward")
+            if self.world > 1:
+                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)         # C3: one flat 6.08 MB bucket, SUM (not mean)
+            self.step_count += 1
+            hp = self.hp
+            _lib.check(L.seunet_adamw_step(p_(self.flat), p_(self.grads), p_(self.m), p_(self.v), self.flat.numel(), hp["lr"],
+                                           hp["betas"][0], hp["betas"][1], hp["eps"], hp["weight_decay"], self.step_count, 1.0,
+                                           self.skip_off, self.skip_len, st), "seunet_adamw_step")
+            self.flat.add_(0)   # bump the version counter: the in-place C-ABI update is invisible to autograd's bookkeeping
+        self.per_sample_gul = per_sample
+        return self.loss

@@ -1,0 +1,102 @@
+"""CPU tests (no GPU): the oracle against the golden vectors produced by the UNMODIFIED reference module
+(oracle/make_golden.py), live pinning against /root/reference when it is present, loss formulas, window enumeration."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import seunet_oracle as oracle
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+REF = "/root/reference"
+
+
+def test_param_schema_matches_state_dict_layout():
+    shapes = oracle.param_shapes(2, 1)
+    assert len(shapes) == 117
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 1520314
+    assert sum(int(np.prod(s)) for s in oracle.param_shapes(1, 1).values()) == 1519938
+    assert list(shapes)[:5] == ["ec1.conv1.weight", "ec1.conv1.bias", "ec1.conv2.weight", "ec1.conv2.bias", "ec1.conv_se.weight"]
+
+
+@pytest.mark.parametrize("name", ["forward_c2_16.npz", "forward_c1_16x24x16.npz"])
+def test_oracle_forward_reproduces_reference_golden(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    sd = oracle.init_params(int(z["in_channel"]), 1, seed=int(z["seed"]))
+    with torch.no_grad():
+        p0, p1 = oracle.forward(sd, torch.from_numpy(z["x"]))
+    assert np.abs(p0.numpy() - z["pred0"]).max() <= 1e-6
+    assert np.abs(p1.numpy() - z["pred1"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("stage", [1, 2, 3])
+def test_oracle_train_mode_loss_and_gradients_reproduce_reference_golden(stage):
+    z = np.load(os.path.join(GOLDEN, f"train_stage{stage}_c2_16.npz"))
+    sd = {k: v.requires_grad_(True) for k, v in oracle.init_params(2, 1, seed=int(z["seed"])).items()}
+    x = torch.from_numpy(z["x"])
+    torch.manual_seed(int(z["torch_seed"]))
+    d0 = oracle.drop_scale(x.shape[0], 24)          # same draw order as SE_UNet.py:232-233
+    d1 = oracle.drop_scale(x.shape[0], 12)
+    p0, p1 = oracle.forward(sd, x, d0, d1)
+    assert np.abs(p0.detach().numpy() - z["pred0"]).max() <= 1e-5
+    loss = oracle.stage_loss(stage, p0, p1, torch.from_numpy(z["label"]), torch.from_numpy(z["weight"]), torch.from_numpy(z["skel"]))
+    assert abs(loss.item() - float(z["loss"])) <= 1e-5
+    loss.backward()
+    for k, v in sd.items():
+        if k == "dc62.conv1.weight":
+            assert v.grad is None
+            continue
+        ref_norm = float(z["gnorm." + k])
+        if k.endswith("conv1.bias"):
+            assert v.grad.abs().max().item() < 1e-6
+            continue
+        assert abs(v.grad.double().norm().item() - ref_norm) <= 2e-3 * ref_norm + 1e-9, k
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "SE_UNet.py")), reason="reference checkout not present on this box")
+def test_oracle_pinned_live_against_reference_module():
+    import importlib.util
+    sys.dont_write_bytecode = True
+    spec = importlib.util.spec_from_file_location("ref_SE_UNet", os.path.join(REF, "SE_UNet.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    sd = oracle.init_params(2, 1, seed=5)
+    m = ref.SE_UNet(2, 1)
+    m.load_state_dict(sd, strict=True)
+    m.eval()
+    x = torch.rand(1, 2, 16, 24, 16, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        r0, r1 = m(x)
+        p0, p1 = oracle.forward(sd, x)
+    assert torch.equal(r0, p0) and torch.equal(r1, p1)
+
+
+def test_loss_closed_form_gradients_match_autograd():
+    """closed-form d loss / d p for Dice, GUL and ATR (what the fused loss kernel implements)."""
+    g = torch.Generator().manual_seed(0)
+    p = torch.rand(2, 1, 4, 4, 4, generator=g, dtype=torch.float64).requires_grad_(True)
+    t = (torch.rand(2, 1, 4, 4, 4, generator=g) > 0.7).double()
+    w = torch.rand(2, 1, 4, 4, 4, generator=g, dtype=torch.float64) + 0.5
+    s = t * (torch.rand(2, 1, 4, 4, 4, generator=g) > 0.5).double()
+    (gd,) = torch.autograd.grad(oracle.dice_loss(p, t), p)
+    I, P, T = (p * t).sum(), p.sum(), t.sum()
+    assert torch.allclose(gd, -2 * t / (P + T + 1) + (2 * I + 1) / (P + T + 1) ** 2)
+    (gg,) = torch.autograd.grad(oracle.general_union_loss_lib(p, t, w), p)
+    A, Bs = (w * (p + 1e-4) ** 0.7 * t).sum(), (w * (0.2 * p + 0.8 * t)).sum()
+    assert torch.allclose(gg, -0.7 * w * t * (p + 1e-4) ** -0.3 / (Bs + 1) + 0.2 * w * (A + 1) / (Bs + 1) ** 2)
+    (ga,) = torch.autograd.grad(oracle.atr_loss(p, t, s, w), p)
+    Ia, Ja = (w * p * s * s).sum(), (w * (p * s + s)).sum()
+    assert torch.allclose(ga, -w * s * s / (Ja + 1) + w * s * (Ia + 1) / (Ja + 1) ** 2)
+
+
+def test_window_enumeration_matches_prediction_py():
+    assert oracle.window_starts(512) == [0, 64, 128, 192, 256, 320, 384]
+    assert oracle.window_starts(400) == [0, 64, 128, 192, 256, 272]      # last window clamped (prediction.py:86-100)
+    assert oracle.window_starts(128) == [0]
+    from se_unet_airseg_b200.inference import window_starts, coverage_counts
+    for n in (128, 129, 200, 400, 512):
+        assert window_starts(n) == oracle.window_starts(n)
+    c = coverage_counts(400, window_starts(400), 128)
+    assert c.min() >= 1 and c[300] == 3
