@@ -95,7 +95,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   auto tempty_bar = [&](int i) { return bar_addr + 8u * (50 + i); };
   const uint32_t tmem_slot_addr = bar_addr + 8u * 52;
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle so that the compiler KNOWS it is warp-uniform: the role branches and everything
+  // inside them (loop counters, descriptors) can then live in uniform registers, which UTCHMMA needs anyway.
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -114,6 +116,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot_addr));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   const bool resident = a.nchunks <= a.wslots;
   const int nq = DT + 2 * a.dil;  // candidate input planes per tile (dil == 0 for pointwise)

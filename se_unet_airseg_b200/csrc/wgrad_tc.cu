@@ -38,7 +38,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const uint32_t tmem_slot_addr = bar_addr + 8u * 17;
   const uint32_t count_addr = bar_addr + 8u * 18;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (see conv_tc.cu)
+  const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.nstages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
     mbar_init(done_bar, 1);
@@ -52,6 +53,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot_addr));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   const int pass = blockIdx.x / a.ctas_per_pass;
   const int rank = blockIdx.x % a.ctas_per_pass;
