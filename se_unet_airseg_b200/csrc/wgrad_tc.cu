@@ -6,7 +6,9 @@
 // ((8,1,m),(8,k)):((1,8,SBO),(8,LBO)): 8 channels contiguous (16 B), 8 consecutive w voxels 16 B apart form a core
 // matrix, the next 8 voxels (next h line) are LBO away, the next 8 channels (next chunk plane) SBO away.  So, exactly
 // as in the forward kernel, one TMA box per input plane feeds all kw taps by start-address offsets.
-//   * UMMA M = 128 input channels (16 chunk planes; planes beyond Cin read junk whose rows are never used),
+//   * UMMA M = 128 input channels (16 chunk planes), or M = 64 when Cin <= 64 (8 planes: half the shared-memory
+//     traffic; its accumulator rows live in TMEM lanes (r/16)*32 + r%16, measured); planes beyond Cin read junk whose
+//     rows are never used,
 //     N = Cout (16/32/64), K = 16 voxels (two h lines of the 16x8 tile) -> 8 MMAs per (tile plane, tap).
 //   * A pass fixes (kd, kh) - 9 passes for 3x3x3 - and keeps the three kw accumulators [128 x 3*Cout] in TMEM for
 //     the whole kernel: the accumulation over ALL voxels of the CTA's tile planes happens inside TMEM (fp32).
@@ -88,7 +90,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else if (warp == 1) {
     uint32_t st = 0, ph = 0, any = 0;
-    const uint32_t idesc = umma_idesc2(a.fmt_a, a.fmt_b, 1u, 1u, 128, COUT);
+    const uint32_t idesc = umma_idesc2(a.fmt_a, a.fmt_b, 1u, 1u, a.m64 ? 64 : 128, COUT);
     const uint32_t line_bytes = (uint32_t)a.lineW * 16u;
     for (int tp = rank; tp < a.numTilePlanes; tp += a.ctas_per_pass) {
       int n, p, h0, w0;
@@ -152,7 +154,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
 // dW[co][ci][kd][kh][kw] = sum_r partial[pass(kd,kh) or ci-block][r][kw][ci][co]   (fixed summation order)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cin, int Cout, int COUT,
-                                    int ksize, int ctas_per_pass, const float* __restrict__ inv_scale) {
+                                    int ksize, int ctas_per_pass, const float* __restrict__ inv_scale, int m64) {
   const float mul = inv_scale ? inv_scale[0] : 1.f;
   const int K3 = ksize * ksize * ksize;
   const int total = Cout * Cin * K3;
@@ -161,6 +163,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     int pass, kw, row;
     if (ksize == 3) { pass = tap / 3; kw = tap % 3; row = ci; }
     else { pass = ci / 128; kw = 0; row = ci % 128; }
+    // UMMA M=64 accumulators use 16 TMEM lanes of each of the four 32-lane sub-partitions
+    if (m64 == 1) row = (row >> 4) * 32 + (row & 15);
     const int ntap = ksize == 3 ? 3 : 1;
     float s = 0.f;
     for (int r = 0; r < ctas_per_pass; ++r)
@@ -233,6 +237,7 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   if (L->smem_bytes > 224u * 1024u) { seunet_set_error("wgrad: shared memory budget exceeded (%u)", L->smem_bytes); return 1; }
   a.partial = partial;
   a.fmt_a = x_bf16 ? 1u : (uint32_t)SEUNET_UMMA_FMT;
+  a.m64 = (ksize == 3 ? Cin <= 64 : (Cin <= 64)) ? 1 : 0;   // UMMA M=64 when 8 chunk planes cover all input channels
   a.fmt_b = a.fmt_a;  // tcgen05 kind::f16 requires A and B in the SAME format (mixed f16 x bf16 is an illegal instruction)
   if (geometry_only) return 0;
   if (ksize == 1 && x_chunk_off + npass * 16 > x_chunks_total + 15) { seunet_set_error("wgrad: bad 1x1 channel blocks"); return 1; }
@@ -279,7 +284,7 @@ int wgrad_launch_run(const WgradLaunch& L, float* dw, const float* inv_scale, cu
   if (rc) return rc;
   const int total = L.Cout * L.Cin * L.ksize * L.ksize * L.ksize;
   wgrad_reduce_kernel<<<std::min((total + 255) / 256, 592), 256, 0, st>>>(L.a.partial, dw, L.Cin, L.Cout, L.COUT, L.ksize,
-                                                                           L.a.ctas_per_pass, inv_scale);
+                                                                           L.a.ctas_per_pass, inv_scale, L.a.m64);
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
