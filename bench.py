@@ -156,7 +156,7 @@ def run_ours(args):
 
     torch.manual_seed(777)
     model = SE_UNet(2, 1).to(dev).eval()
-    sw = SlidingWindowPredictor(model, CUBE, STRIDE, batch=args.batch)
+    sw = SlidingWindowPredictor(model, CUBE, STRIDE, batch=args.batch, streams=args.streams)
     img_host = synthetic_ct(VOL, seed=777 + rank).pin_memory()
     img_dev = img_host.to(dev)
     vox = VOL[0] * VOL[1] * VOL[2]
@@ -256,7 +256,7 @@ def run_ours(args):
         "dtype": "f16" if L.seunet_act_dtype() == 0 else "bf16", "data": "synthetic",
         "config": {"workload": "sliding-window SE_UNet inference of one synthetic 512x512x400 CT volume per GPU "
                                "(294 windows of 128^3 at stride 64, eval mode, threshold 0.5)",
-                   "in_channel": 2, "window_batch": args.batch, "windows_per_volume": nwin,
+                   "in_channel": 2, "window_batch": args.batch, "streams": args.streams, "windows_per_volume": nwin,
                    "l2": "inputs larger than L2: every window forward streams > 1 GB of activations through a 126 MB L2",
                    "accumulate": "fp32", "storage": "fp16 activations/weights, fp32 accumulate/statistics"},
         "clocks": clocks,
@@ -285,6 +285,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=6, help="windows per forward (294 = 6 * 49)")
+    ap.add_argument("--streams", type=int, default=2, help="CUDA streams alternating over window batches (overlaps HBM-bound and tensor-bound kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -138,7 +138,7 @@ class _Plan:
             pass
 
 
-_MAX_PLANS = 4
+_MAX_PLANS = 6
 
 
 class _SEUNetFunction(torch.autograd.Function):
@@ -301,9 +301,10 @@ class SE_UNet(nn.Module):
             rt.flat_src = src
         return rt.flat
 
-    def _plan(self, batch, D, H, W, mode, device):
+    def _plan(self, batch, D, H, W, mode, device, slot=0):
+        """Bound plan for this shape; `slot` selects independent workspaces (concurrent streams)."""
         rt = self._runtime()
-        key = (batch, D, H, W, self.in_channel, self.n_classes, mode, device.index)
+        key = (batch, D, H, W, self.in_channel, self.n_classes, mode, device.index, slot)
         plan = rt.plans.get(key)
         if plan is None:
             while len(rt.order) >= _MAX_PLANS:

@@ -45,9 +45,13 @@ def coverage_counts(length, starts, cube):
 class SlidingWindowPredictor:
     """Runs `model` (se_unet_airseg_b200.SE_UNet on a CUDA device, eval mode like prediction.py:64) over a CT volume."""
 
-    def __init__(self, model, cube=128, step=64, batch=6, threshold=0.5):
+    def __init__(self, model, cube=128, step=64, batch=6, threshold=0.5, streams=2):
+        """streams > 1: consecutive window batches run on different CUDA streams with their own plan workspaces, so the
+        HBM-bound passes of one batch overlap the tensor-bound convolutions of the other (both fit on an SM together)."""
         self.model = model
         self.cube, self.step, self.batch, self.threshold = cube, step, batch, threshold
+        self.nstreams = max(1, streams)
+        self._streams = None
         self._geom = None
 
     def _geometry(self, shape, device):
@@ -90,20 +94,39 @@ class SlidingWindowPredictor:
         wins = g["wins"]
         params = m._param_tensors()
         flat = m._flat_params(params)
-        i = 0
+        main = torch.cuda.current_stream(dev)
+        if self._streams is None or self._streams[0].device != dev:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.nstreams)] if self.nstreams > 1 else [main]
+        streams = self._streams
+        if self.nstreams > 1:
+            ready = torch.cuda.Event()
+            ready.record(main)
+            for s_ in streams:
+                s_.wait_event(ready)
+        i, k = 0, 0
         while i < len(wins):
             b = min(self.batch, len(wins) - i)
-            plan = m._plan(b, cube, cube, cube, 0, dev)
-            plan.pack(flat)
-            ones0, ones1, pred0, pred1 = self._buffers(plan, b, dev)
-            offs = (ctypes.c_int64 * b)(*[w[0] * sD + w[1] * sH + w[2] * sW for w in wins[i:i + b]])
-            strides = (ctypes.c_int64 * 5)(0, sC, sD, sH, sW)
-            _lib.check(L.seunet_forward(plan.handle, _lib.ptr(x2), strides, offs, _lib.ptr(flat), _lib.ptr(ones0),
-                                        _lib.ptr(ones1), _lib.ptr(pred0), _lib.ptr(pred1), st), "seunet_forward")
-            starts = (ctypes.c_int * (3 * b))(*[v for w in wins[i:i + b] for v in w])
-            _lib.check(L.seunet_window_accumulate(_lib.ptr(pred1), starts, b, cube, cube, cube, _lib.ptr(g["acc"]),
-                                                  X, Y, Z, 1, st), "seunet_window_accumulate")
+            slot = k % len(streams)
+            cs = streams[slot]
+            with torch.cuda.stream(cs):
+                stp = ctypes.c_void_p(cs.cuda_stream)
+                plan = m._plan(b, cube, cube, cube, 0, dev, slot=slot)
+                plan.pack(flat)
+                ones0, ones1, pred0, pred1 = self._buffers(plan, b, dev)
+                offs = (ctypes.c_int64 * b)(*[w[0] * sD + w[1] * sH + w[2] * sW for w in wins[i:i + b]])
+                strides = (ctypes.c_int64 * 5)(0, sC, sD, sH, sW)
+                _lib.check(L.seunet_forward(plan.handle, _lib.ptr(x2), strides, offs, _lib.ptr(flat), _lib.ptr(ones0),
+                                            _lib.ptr(ones1), _lib.ptr(pred0), _lib.ptr(pred1), stp), "seunet_forward")
+                starts = (ctypes.c_int * (3 * b))(*[v for w in wins[i:i + b] for v in w])
+                _lib.check(L.seunet_window_accumulate(_lib.ptr(pred1), starts, b, cube, cube, cube, _lib.ptr(g["acc"]),
+                                                      X, Y, Z, 1, stp), "seunet_window_accumulate")
             i += b
+            k += 1
+        if self.nstreams > 1:
+            for s_ in streams:
+                done = torch.cuda.Event()
+                done.record(s_)
+                main.wait_event(done)
         _lib.check(L.seunet_window_finalize(_lib.ptr(g["acc"]), _lib.ptr(g["counts"]), X, Y, Z, float(self.threshold),
                                             _lib.ptr(g["mask"]), 1 if return_prob else 0, st), "seunet_window_finalize")
         return (g["mask"], g["acc"]) if return_prob else g["mask"]
