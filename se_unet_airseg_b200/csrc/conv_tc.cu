@@ -55,23 +55,22 @@ __device__ __forceinline__ int slot_plane(int slot, int dil) {
   return dil == 2 ? ((slot % (DT / 2)) * 2 + slot / (DT / 2)) : slot;
 }
 
-// Range [jlo, jhi] of stacked kd blocks (j=0 -> kd=2 -> output plane q-dil, j=1 -> q, j=2 -> q+dil)
-// that are valid for tile-relative input plane q_rel.  Returns false when the plane is not needed.
-template <int DT>
-__device__ __forceinline__ bool plane_jrange(const ConvKArgs& a, int d0, int q_rel, int& jlo, int& jhi) {
+// Stacked kd blocks (j=0 -> kd=2 -> output plane q-dil, j=1 -> q, j=2 -> q+dil) that are valid for the tile-relative
+// input plane q_rel: first block jlo, count nj (valid blocks are always contiguous), first output plane p_lo.
+// dteff = number of valid output planes of this tile.  Returns false when the plane is not needed at all.
+__device__ __forceinline__ bool plane_blocks(int nkd, int dil, int D, int d0, int dteff, int q_rel, int& jlo, int& nj, int& p_lo) {
   const int q = d0 + q_rel;
-  jlo = 3; jhi = -1;
-  if (q < 0 || q >= a.D) return false;
-  if (a.nkd == 1) {
-    jlo = jhi = 0;
-    return q_rel >= 0 && q_rel < DT;
+  if (q < 0 || q >= D) return false;
+  if (nkd == 1) {
+    jlo = 0; nj = 1; p_lo = q_rel;
+    return q_rel < dteff;
   }
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const int p = q_rel + (j - 1) * a.dil;
-    if (p >= 0 && p < DT && d0 + p < a.D) { jlo = min(jlo, j); jhi = max(jhi, j); }
-  }
-  return jhi >= 0;
+  const int p0 = q_rel - dil, p2 = q_rel + dil;
+  const int v0 = (p0 >= 0) & (p0 < dteff), v1 = (q_rel >= 0) & (q_rel < dteff), v2 = (p2 >= 0) & (p2 < dteff);
+  nj = v0 + v1 + v2;
+  jlo = v0 ? 0 : (v1 ? 1 : 2);
+  p_lo = q_rel + (jlo - 1) * dil;
+  return nj != 0;
 }
 
 template <int COUT>
@@ -94,6 +93,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   auto tfull_bar = [&](int i) { return bar_addr + 8u * (48 + i); };
   auto tempty_bar = [&](int i) { return bar_addr + 8u * (50 + i); };
   const uint32_t tmem_slot_addr = bar_addr + 8u * 52;
+  const uint32_t zero_addr = bar_addr + 512u;   // 128 zero bytes: operands of the accumulator-clearing UMMA
 
   // warp index through a shuffle so that the compiler KNOWS it is warp-uniform: the role branches and everything
   // inside them (loop counters, descriptors) can then live in uniform registers, which UTCHMMA needs anyway.
@@ -107,6 +107,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     fence_mbar_init();
     tma_prefetch_desc(&tmap);
   }
+  if (threadIdx.x < 32) asm volatile("st.shared.u32 [%0], %1;" ::"r"(zero_addr + 4u * threadIdx.x), "r"(0u) : "memory");
+  fence_proxy_async();   // generic-proxy zeros must be visible to the tensor core (async proxy)
   if (warp == 1) {
     tmem_alloc(tmem_slot_addr, 512);
     tmem_relinquish();
@@ -147,9 +149,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             ++wcount;
           }
           for (int qi = 0; qi < nq; ++qi) {
-            int jlo, jhi;
+            int jlo, nj, p_lo;
             const int q_rel = qi - a.dil;
-            if (!plane_jrange<DT>(a, t.d0, q_rel, jlo, jhi)) continue;
+            if (!plane_blocks(a.nkd, a.dil, a.D, t.d0, min(DT, a.D - t.d0), q_rel, jlo, nj, p_lo)) continue;
             mbar_wait(empty_bar(st), ph ^ 1u);
             mbar_expect_tx(full_bar(st), a.box_bytes);
             tma_load_4d(s_addr + st * a.stage_bytes, &tmap, full_bar(st),
@@ -169,11 +171,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const uint32_t idesc1 = umma_idesc(a.fmt, 128, COUT);
       const uint32_t idesc2 = umma_idesc(a.fmt, 128, 2 * COUT);
       const uint32_t idesc3 = umma_idesc(a.fmt, 128, 3 * COUT);
+      const uint32_t idesc_clear = umma_idesc(a.fmt, 128, kConvAccCols);
+      const uint64_t zdesc = umma_desc(zero_addr, 0, 0);   // every core matrix reads the same 128 zero bytes
+      const int dil = a.dil, nkd = a.nkd, nsteps = a.nsteps;
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<DT>(a, tile);
+        const int dteff = min(DT, a.D - t.d0);
         mbar_wait(tempty_bar(acc), accph ^ 1u);
         tc_fence_after();
-        uint32_t touched = 0;
+        const uint32_t dstage = tmem_base + acc * kConvAccCols;
+        // Clear the whole accumulator stage with one UMMA (D = 0 x 0, accumulate off).  Every later instruction then
+        // accumulates unconditionally, so the kd-stacked accumulators need no first-touch bookkeeping.
+        if (elect_one_sync()) umma_f16(dstage, zdesc, zdesc, idesc_clear, 0u);
         for (int c = 0; c < a.nchunks; ++c) {
           int slot;
           if (resident) {
@@ -185,33 +194,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           }
           const uint32_t wsm = w_addr + slot * a.wchunk_bytes;
           for (int qi = 0; qi < nq; ++qi) {
-            int jlo, jhi;
-            const int q_rel = qi - a.dil;
-            if (!plane_jrange<DT>(a, t.d0, q_rel, jlo, jhi)) continue;
-            const int nj = jhi - jlo + 1;
-            const int p_lo = (a.nkd == 1) ? q_rel : q_rel + (jlo - 1) * a.dil;
-            const int slot_lo = plane_slot<DT>(p_lo, a.dil);
-            const uint32_t dcol = tmem_base + acc * kConvAccCols + slot_lo * COUT;
+            int jlo, nj, p_lo;
+            const int q_rel = qi - dil;
+            if (!plane_blocks(nkd, dil, a.D, t.d0, dteff, q_rel, jlo, nj, p_lo)) continue;
+            const uint32_t dcol = dstage + plane_slot<DT>(p_lo, dil) * COUT;
             const uint32_t idesc = nj == 3 ? idesc3 : (nj == 2 ? idesc2 : idesc1);
             mbar_wait(full_bar(st), ph);
             tc_fence_after();
             const uint64_t abase = umma_desc(s_addr + st * a.stage_bytes, 0, a.a_sbo);
             const uint64_t bbase = umma_desc(wsm + jlo * COUT * 16, a.b_lbo, 128);
-            int s0 = 0;
-            if (c == 0) {
-              // first contribution of this input plane: the stacked accumulators may differ in
-              // whether they were written before, so issue one N=COUT instruction per plane.
-              const uint64_t adesc = abase + a.a_delta[0];
-              for (int jj = 0; jj < nj; ++jj) {
-                const int sl = slot_lo + jj;
-                const uint64_t bdesc = bbase + a.b_delta[0] + (uint64_t)(jj * COUT);
-                if (elect_one_sync()) umma_f16(dcol + jj * COUT, adesc, bdesc, idesc1, (touched >> sl) & 1u);
-                touched |= 1u << sl;
-              }
-              s0 = 1;
-            }
 #pragma unroll 4
-            for (int s = s0; s < a.nsteps; ++s) {
+            for (int s = 0; s < nsteps; ++s) {
               const uint64_t adesc = abase + a.a_delta[s];
               const uint64_t bdesc = bbase + a.b_delta[s];
               if (elect_one_sync()) umma_f16(dcol, adesc, bdesc, idesc, 1u);
@@ -373,7 +366,7 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, uint16_t* __restri
 // host
 // ---------------------------------------------------------------------------------------------
 static constexpr uint32_t kSmemBudget = 222u * 1024u;  // + 2 KB static smem (s_run) + alignment slack <= 227 KB
-static constexpr uint32_t kBarBytes = 8u * 64u;
+static constexpr uint32_t kBarBytes = 8u * 64u + 128u;   // barriers + the 128-byte zero block
 
 int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil, int bf16) {
   memset(g, 0, sizeof(*g));

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) upsample2_kernel(const act_t* __restrict_
   st_chunk(dst + (((size_t)n * dst_chunks + dst_off + k) * Vo + v) * 8, floats_to_chunk(acc));
 }
 
-int launch_upsample2(const act_t* src, int C, Dims sd, act_t* dst, int dst_chunks, int dst_off, cudaStream_t st) {
+static int launch_upsample2_v0(const act_t* src, int C, Dims sd, act_t* dst, int dst_chunks, int dst_off, cudaStream_t st) {  // superseded by pointwise2.cu
   const long long Vo = dims_vox(sd) * 8;
   dim3 grid((unsigned)((Vo + 255) / 256), C / 8, sd.N);
   upsample2_kernel<<<grid, 256, 0, st>>>(src, sd, dst, dst_chunks, dst_off, C / 8);
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(256) head_kernel(const __grid_constant__ HeadA
   a.pred1[(size_t)n * V + v] = p1;
 }
 
-int launch_head(const HeadArgs& a, cudaStream_t st) {
+static int launch_head_v0(const HeadArgs& a, cudaStream_t st) {  // superseded by pointwise2.cu
   const long long V = dims_vox(a.d);
   dim3 grid((unsigned)((V + 255) / 256), a.d.N);
   head_kernel<<<grid, 256, 0, st>>>(a);
