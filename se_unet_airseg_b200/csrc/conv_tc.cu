@@ -87,13 +87,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   const uint32_t bar_addr = s_addr + a.nstages * a.stage_bytes;
   // barrier slots (8 bytes each)
   auto full_bar = [&](int i) { return bar_addr + 8u * i; };
-  auto empty_bar = [&](int i) { return bar_addr + 8u * (16 + i); };
-  auto wfull_bar = [&](int i) { return bar_addr + 8u * (32 + i); };
-  auto wempty_bar = [&](int i) { return bar_addr + 8u * (40 + i); };
-  auto tfull_bar = [&](int i) { return bar_addr + 8u * (48 + i); };
-  auto tempty_bar = [&](int i) { return bar_addr + 8u * (50 + i); };
-  const uint32_t tmem_slot_addr = bar_addr + 8u * 52;
-  const uint32_t zero_addr = bar_addr + 512u;   // 128 zero bytes: operands of the accumulator-clearing UMMA
+  auto empty_bar = [&](int i) { return bar_addr + 8u * (kConvMaxStages + i); };
+  auto wfull_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + i); };
+  auto wempty_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 8 + i); };
+  auto tfull_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 16 + i); };
+  auto tempty_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 18 + i); };
+  const uint32_t tmem_slot_addr = bar_addr + 8u * (2 * kConvMaxStages + 20);
+  const uint32_t zero_addr = bar_addr + 8u * (2 * kConvMaxStages + 32);   // 128 zero bytes: operands of the accumulator-clearing UMMA
 
   // warp index through a shuffle so that the compiler KNOWS it is warp-uniform: the role branches and everything
   // inside them (loop counters, descriptors) can then live in uniform registers, which UTCHMMA needs anyway.
@@ -366,7 +366,7 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, uint16_t* __restri
 // host
 // ---------------------------------------------------------------------------------------------
 static constexpr uint32_t kSmemBudget = 222u * 1024u;  // + 2 KB static smem (s_run) + alignment slack <= 227 KB
-static constexpr uint32_t kBarBytes = 8u * 64u + 128u;   // barriers + the 128-byte zero block
+static constexpr uint32_t kBarBytes = 8u * (2 * kConvMaxStages + 32) + 128u;   // barriers + the 128-byte zero block
 
 int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil, int bf16) {
   memset(g, 0, sizeof(*g));
@@ -425,7 +425,8 @@ int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil,
   g->stage_bytes = (g->box_bytes + 127u) & ~127u;
   const uint32_t wregion = ((uint32_t)g->wslots * g->wchunk_bytes + 127u) & ~127u;
   int nst = (int)((kSmemBudget - wregion - kBarBytes - 128u) / g->stage_bytes);
-  nst = std::min(nst, 12);
+  // TMA is latency-bound: keep >= ~96 KB in flight per SM when the stages are small (ec1/ec2: 2.9 KB per plane)
+  nst = std::min(nst, std::max(4, std::min(kConvMaxStages, (int)(98304u / g->stage_bytes))));
   if (nst < 2) { seunet_set_error("conv: shared memory budget exceeded"); return 1; }
   g->nstages = nst;
   g->smem_bytes = wregion + nst * g->stage_bytes + kBarBytes + 128u;

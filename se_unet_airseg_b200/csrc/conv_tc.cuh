@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 constexpr int kConvThreads = 192;   // warp 0: TMA producer, warp 1: UMMA issuer, warps 2-5: epilogue
+constexpr int kConvMaxStages = 32;  // activation stage ring (mbarrier slots)
 constexpr int kConvMaxSteps = 40;   // UMMA K=16 steps per (input plane, channel chunk)
 constexpr int kConvTileH = 16;      // one UMMA M=128 block = 16 (h) x 8 (w) voxels of one d-plane
 constexpr int kConvTileW = 8;

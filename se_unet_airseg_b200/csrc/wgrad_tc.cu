@@ -78,39 +78,37 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       for (int tp = rank; tp < a.numTilePlanes; tp += a.ctas_per_pass) {
         int n, p, h0, w0;
         decode(tp, n, p, h0, w0);
-        const int q = p + dshift;
-        if (q < 0 || q >= a.D) continue;
+        // tile plane `p` indexes the INPUT plane; it pairs with output-gradient plane p - dshift
+        const int po = p - dshift;
+        if (po < 0 || po >= a.D) continue;
         mbar_wait(empty_bar(st), ph ^ 1u);
-        mbar_expect_tx(full_bar(st), a.x_box_bytes + a.dy_box_bytes);
-        tma_load_4d(x_addr + st * a.x_stage_bytes, &tmap_x, full_bar(st), 8 * (w0 - a.dil), h0 + hshift, q,
-                    n * a.x_chunks_total + x_chunk);
-        tma_load_4d(dy_addr + st * a.dy_stage_bytes, &tmap_dy, full_bar(st), 8 * w0, h0, p, n * a.dy_chunks_total + a.dy_chunk_off);
+        mbar_expect_tx(full_bar(st), a.x_box_bytes + ntap * a.dy_box_bytes);
+        tma_load_4d(x_addr + st * a.x_stage_bytes, &tmap_x, full_bar(st), 8 * w0, h0, p, n * a.x_chunks_total + x_chunk);
+        for (int kw = 0; kw < ntap; ++kw)   // dY shifted against the taps: X[u] pairs with dY[u - shift(kd,kh,kw)]
+          tma_load_4d(dy_addr + st * a.dy_stage_bytes + kw * a.dy_box_bytes, &tmap_dy, full_bar(st),
+                      8 * (w0 - (kw - (ntap == 3 ? 1 : 0)) * a.dil), h0 - hshift, po, n * a.dy_chunks_total + a.dy_chunk_off);
         if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     uint32_t st = 0, ph = 0, any = 0;
-    const uint32_t idesc = umma_idesc2(a.fmt_a, a.fmt_b, 1u, 1u, a.m64 ? 64 : 128, COUT);
-    const uint32_t line_bytes = (uint32_t)a.lineW * 16u;
+    const uint32_t idesc = umma_idesc2(a.fmt_a, a.fmt_b, 1u, 1u, a.m64 ? 64 : 128, ntap * COUT);
     for (int tp = rank; tp < a.numTilePlanes; tp += a.ctas_per_pass) {
       int n, p, h0, w0;
       decode(tp, n, p, h0, w0);
-      const int q = p + dshift;
-      if (q < 0 || q >= a.D) continue;
+      const int po = p - dshift;
+      if (po < 0 || po >= a.D) continue;
       mbar_wait(full_bar(st), ph);
       tc_fence_after();
-      // A: MN-major, m-groups (chunk planes) SBO = plane pitch, k-groups (h lines) LBO = line pitch
-      const uint64_t abase = umma_desc(x_addr + st * a.x_stage_bytes, line_bytes, a.x_plane_bytes);
-      // B: MN-major, n-groups (chunk planes of dY) SBO = 128 voxels * 16 B, k-groups (h lines) LBO = 8 voxels * 16 B
-      const uint64_t bbase = umma_desc(dy_addr + st * a.dy_stage_bytes, 128u, 2048u);
-      for (int kw = 0; kw < ntap; ++kw) {
-        const uint32_t a_tap = (uint32_t)(kw * a.dil) * 16u;
+      // A (X tile, 16x8 voxels, no halo) and B (ntap shifted dY tiles stacked along N): MN-major, m/n-groups = chunk planes
+      // 2048 B apart (SBO), k-groups = h lines 128 B apart (LBO)
+      uint64_t adesc = umma_desc(x_addr + st * a.x_stage_bytes, 128u, 2048u);
+      uint64_t bdesc = umma_desc(dy_addr + st * a.dy_stage_bytes, 128u, 2048u);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint64_t adesc = abase + (uint64_t)((a_tap + 2u * j * line_bytes) >> 4);
-          const uint64_t bdesc = bbase + (uint64_t)((2u * j * 128u) >> 4);
-          if (elect_one_sync()) umma_f16(tmem_base + kw * COUT, adesc, bdesc, idesc, (any | (uint32_t)j) != 0u ? 1u : 0u);
-        }
+      for (int j = 0; j < 8; ++j) {
+        if (elect_one_sync()) umma_f16(tmem_base, adesc, bdesc, idesc, (any | (uint32_t)j) != 0u ? 1u : 0u);
+        adesc += 16u;   // two h lines = 256 B
+        bdesc += 16u;
       }
       any = 1;
       if (elect_one_sync()) umma_commit(empty_bar(st));
@@ -219,18 +217,18 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   const int xplanes = std::min(16, cin_planes_total);
   a.x_chunks_total = x_chunks_total; a.x_chunk_off = x_chunk_off;
   a.dy_chunks_total = dy_chunks_total; a.dy_chunk_off = dy_chunk_off;
-  a.x_plane_bytes = 16u * a.lineW * 16u;
+  a.x_plane_bytes = 2048u;   // 16 x 8 voxels x 16 B, no halo: the tap shifts are applied to dY
   a.x_box_bytes = a.x_plane_bytes * xplanes;
   a.x_stage_bytes = (a.x_box_bytes + 127u) & ~127u;
   a.dy_box_bytes = 128u * L->COUT * 2u;
-  a.dy_stage_bytes = a.dy_box_bytes;
+  a.dy_stage_bytes = (ksize == 3 ? 3u : 1u) * a.dy_box_bytes;
   int nst = (int)((200u * 1024u) / (a.x_stage_bytes + a.dy_stage_bytes));
   nst = std::min(nst, 6);
   if (nst < 2) { seunet_set_error("wgrad: shared memory budget exceeded"); return 1; }
   a.nstages = nst;
   uint32_t natural = nst * (a.x_stage_bytes + a.dy_stage_bytes);
   // junk rows: an M=128 A operand spans 16 chunk planes from the start of the LAST X stage
-  const uint32_t junk_end = (nst - 1) * a.x_stage_bytes + 16u * a.x_plane_bytes + 8u * a.lineW * 16u;
+  const uint32_t junk_end = (nst - 1) * a.x_stage_bytes + 16u * a.x_plane_bytes;
   natural = std::max(natural, junk_end);
   a.bar_off = (natural + 127u) & ~127u;
   L->smem_bytes = a.bar_off + 256u + 128u;
@@ -247,7 +245,7 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   {
     cuuint64_t gdim[4] = {(cuuint64_t)8 * W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N * x_chunks_total};
     cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-    cuuint32_t box[4] = {(cuuint32_t)(8 * a.lineW), 16u, 1u, (cuuint32_t)xplanes};
+    cuuint32_t box[4] = {64u, 16u, 1u, (cuuint32_t)xplanes};
     CUresult r = enc(&L->tmap_x, x_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
                      const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

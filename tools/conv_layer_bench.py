@@ -30,7 +30,7 @@ for name, cin, cout, k, dil, lvl in LAYERS:
     stats = torch.zeros(B * COUT * 2, dtype=torch.float64, device=dev)
     scratch = torch.empty(L.seunet_conv_scratch_bytes(cin, cout, k, dil), dtype=torch.uint8, device=dev)
     run = lambda: _lib.check(L.seunet_conv_fprop(_lib.ptr(xin), chunks, 0, _lib.ptr(w), B, s, s, s, cin, cout, k, dil,
-                                                 _lib.ptr(out), _lib.ptr(stats), _lib.ptr(scratch), 0, st), "conv")
+                                                 _lib.ptr(out), _lib.ptr(stats), _lib.ptr(scratch), 0, 0, 0, 0, st), "conv")
     for _ in range(2):
         run()
     torch.cuda.synchronize()
