@@ -220,6 +220,40 @@ def run_ours(args):
                 other_ms += ms.value
     L.seunet_plan_set_timing(plan.handle, 0)
 
+    # ------------------------------------------------------------------ secondary metric: DP training step (BASELINE config 3)
+    train = None
+    if not args.no_train and 8 % world == 0:
+        from se_unet_airseg_b200.trainer import DataParallelTrainer
+        del sw
+        model._runtime().plans.clear(); model._runtime().order.clear()
+        torch.cuda.empty_cache()
+        bt = 8 // world                                   # global batch 8 (train.py:167), sharded over the ranks
+        model.train()
+        tr = DataParallelTrainer(model, stage=2)
+        gt = torch.Generator(device=dev).manual_seed(1234 + rank)
+        xt = torch.rand(bt, 2, CUBE, CUBE, CUBE, device=dev, generator=gt)
+        lab = (torch.rand(bt, 1, CUBE, CUBE, CUBE, device=dev, generator=gt) > 0.98).float()
+        wgt = torch.where(lab > 0, torch.rand(lab.shape, device=dev, generator=gt) * 2 + 0.5, torch.ones_like(lab))
+        for _ in range(2):
+            tr.step(xt, lab, wgt)
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        tsteps = 3
+        for _ in range(tsteps):
+            loss_t = tr.step(xt, lab, wgt)
+        t1e.record()
+        barrier()
+        ms_train = t0e.elapsed_time(t1e) / tsteps
+        if world > 1:
+            tt = torch.tensor([ms_train], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_train = tt.item()
+        train = {"metric": "train_patches_per_sec", "value": 8 / (ms_train * 1e-3), "unit": "patches/s", "ms_per_step": ms_train,
+                 "global_batch": 8, "per_rank_batch": bt, "patch": "128^3", "stage": 2, "scaling": "strong",
+                 "step": "forward + GUL loss sums (+NCCL all-reduce) + backward + gradient SUM all-reduce + fused AdamW",
+                 "loss": float(loss_t.item()), "tflops": 1.89e12 * 8 / (ms_train * 1e-3) / 1e12}
+        model.eval()
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -271,6 +305,7 @@ def run_ours(args):
                      "top_layers_ms": dict(sorted(per_layer.items(), key=lambda kv: -kv[1])[:8])},
         "cpu_baseline": cpu,
         "mask_foreground_fraction": fg_frac,
+        "train": train,
         "patches_per_s": world * nwin / (ms_step * 1e-3),
     }
     print(json.dumps(line))
@@ -287,6 +322,7 @@ def main():
     ap.add_argument("--batch", type=int, default=6, help="windows per forward (294 = 6 * 49)")
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams alternating over window batches (overlaps HBM-bound and tensor-bound kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
