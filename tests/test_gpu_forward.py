@@ -98,3 +98,25 @@ def test_forward_matches_golden_reference_vectors():
             p0, p1 = m(x.cuda())
         _compare(p0.cpu(), torch.from_numpy(z["pred0"]), f + ":pred0")
         _compare(p1.cpu(), torch.from_numpy(z["pred1"]), f + ":pred1")
+
+
+def test_forward_full_window_128_matches_oracle_and_is_batch_consistent():
+    """BASELINE config size: one 128^3 window (2,097,152 voxels, 14-42 conv tiles per CTA) against the fp32 oracle, plus
+    the size-independent property that a sample's logits do not depend on what else is in the batch (InstanceNorm is per
+    sample; catches cross-sample leaks in the persistent multi-tile kernels)."""
+    m, sd = _model(2)
+    g = torch.Generator().manual_seed(128)
+    x = torch.rand(2, 2, 128, 128, 128, generator=g)
+    with torch.no_grad():
+        r0, r1 = oracle.forward(sd, x[:1])
+        xb = x.cuda()
+        p0, p1 = m(xb)
+        q0, q1 = m(xb[1:2])
+    e0, a0 = _compare(p0[:1].cpu(), r0, "128^3 pred0")
+    e1, a1 = _compare(p1[:1].cpu(), r1, "128^3 pred1")
+    # Raw mask agreement with RANDOM-INIT weights is a worst case (SURVEY 8d hazard): the logits are N(~0, 0.04), so ~0.1 %
+    # of 2M voxels lie within the 1e-3 logit error of the threshold.  Every voxel with |logit_ref| > 2e-2 agrees (checked
+    # in _compare); the raw figure is printed above and held to 99.8 % here (it is >= 99.9 % on all smaller cases).
+    assert a1 >= 0.998, f"raw thresholded-mask agreement {a1:.5f}"
+    # same kernels, same data, different batch position: only the fp64-atomic summation order may differ
+    assert (p1[1:2] - q1).abs().max().item() <= 1e-4 and (p0[1:2] - q0).abs().max().item() <= 1e-4
