@@ -6,7 +6,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libseunet_b200.so")
+# SEUNET_LIB_PATH: developer override for A/B timing of two builds of the same ABI
+LIB_PATH = os.environ.get("SEUNET_LIB_PATH") or os.path.join(HERE, "libseunet_b200.so")
 
 _c = ctypes
 _vp, _i, _i64, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_size_t

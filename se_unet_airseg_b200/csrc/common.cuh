@@ -224,6 +224,18 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same instruction with the two shared-memory descriptors given as (low, high) 32-bit words: only the low word (start
+// address | LBO) changes from step to step, so the issuing warp does 32-bit uniform adds instead of 64-bit ones.
+__device__ __forceinline__ void umma_f16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ uint32_t elect_one_sync() {
   uint32_t pred = 0;
   asm volatile(

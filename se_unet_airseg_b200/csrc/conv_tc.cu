@@ -25,6 +25,7 @@
 //   * Epilogue: TMEM -> registers -> fp16/bf16 raw conv output (chunk planes) + per-(n,c) sum / sum
 //     of squares for InstanceNorm (fp32 partials from the fp32 accumulators, fp64 atomics).
 #include "conv_tc.cuh"
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
@@ -71,6 +72,40 @@ __device__ __forceinline__ bool plane_blocks(int nkd, int dil, int D, int d0, in
   jlo = v0 ? 0 : (v1 ? 1 : 2);
   p_lo = q_rel + (jlo - 1) * dil;
   return nj != 0;
+}
+
+// The 9 in-plane taps x J 16-channel blocks of one input plane, fully unrolled (J = 0: runtime block count).  Runs on
+// the whole issuer warp with uniform operands; only the tcgen05.mma itself is issued by the elected lane.
+template <int J>
+__device__ __forceinline__ void issue_taps3(uint32_t dcol, uint32_t a_lo_st, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t kh_step, uint32_t kw_step, uint32_t j_step,
+                                            uint32_t b_step, int jsteps) {
+  // Only a few tcgen05.mma per basic block: every in-flight instruction pins its own uniform-register operands, and a
+  // fully unrolled plane (36 of them) pushes the loop-carried state out of the uniform register file.
+  uint32_t a_row = a_lo_st;
+#pragma unroll 1
+  for (int kh = 0; kh < 3; ++kh) {
+    uint32_t a_tap = a_row;
+#pragma unroll 1
+    for (int kw = 0; kw < 3; ++kw) {
+      uint32_t a_lo = a_tap;
+      if (J > 0) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          if (elect_one_sync()) umma_f16_lohi(dcol, a_lo, a_hi, b_lo, b_hi, idesc);
+          a_lo += j_step; b_lo += b_step;
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < jsteps; ++j) {
+          if (elect_one_sync()) umma_f16_lohi(dcol, a_lo, a_hi, b_lo, b_hi, idesc);
+          a_lo += j_step; b_lo += b_step;
+        }
+      }
+      a_tap += kw_step;
+    }
+    a_row += kh_step;
+  }
 }
 
 template <int COUT>
@@ -169,14 +204,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     {
       uint32_t st = 0, ph = 0, wcount = 0, acc = 0, accph = 0, wready = 0;
       const uint32_t idesc1 = umma_idesc(a.fmt, 128, COUT);
-      const uint32_t idesc2 = umma_idesc(a.fmt, 128, 2 * COUT);
-      const uint32_t idesc3 = umma_idesc(a.fmt, 128, 3 * COUT);
+      constexpr uint32_t kIdescNStep = (uint32_t)(COUT >> 3) << 17;   // one more kd block along N
       const uint32_t idesc_clear = umma_idesc(a.fmt, 128, kConvAccCols);
       const uint64_t zdesc = umma_desc(zero_addr, 0, 0);   // every core matrix reads the same 128 zero bytes
-      const int dil = a.dil, nkd = a.nkd, nsteps = a.nsteps;
+      const int dil = a.dil, nkd = a.nkd, D = a.D;
+      const uint32_t a_hi = a.a_hi, b_hi = a.b_hi, stage16 = a.stage16;
+      const uint32_t a_lo_first = a.a_lo0 | ((s_addr & 0x3FFFFu) >> 4);
+      const uint32_t b_lo_lbo = ((a.b_lbo >> 4) & 0x3FFFu) << 16;
+      uint32_t a_lo_st = a_lo_first;          // A descriptor low word of ring stage st
+      uint32_t fbar = full_bar(0);            // full barrier of ring stage st (empty barrier = + 8 * kConvMaxStages)
+      const int regular = a.regular, ntap = a.ntap, jsteps = a.jsteps;
+      // bit mask instead of the count, so that the dispatch below compiles to uniform branches and not to a jump table
+      const int jmode = jsteps == 1 ? 1 : (jsteps == 2 ? 2 : (jsteps == 4 ? 4 : 8));
+      const uint32_t kh_step = a.kh_step, kw_step = a.kw_step, j_step = a.j_step, b_step = a.b_step;
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<DT>(a, tile);
-        const int dteff = min(DT, a.D - t.d0);
+        const int dteff = min(DT, D - t.d0);
         mbar_wait(tempty_bar(acc), accph ^ 1u);
         tc_fence_after();
         const uint32_t dstage = tmem_base + acc * kConvAccCols;
@@ -192,38 +235,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             slot = wcount % a.wslots;
             mbar_wait(wfull_bar(slot), (wcount / a.wslots) & 1u);
           }
-          const uint32_t wsm = w_addr + slot * a.wchunk_bytes;
-          for (int qi = 0; qi < nq; ++qi) {
-            int jlo, nj, p_lo;
-            const int q_rel = qi - dil;
-            if (!plane_blocks(nkd, dil, a.D, t.d0, dteff, q_rel, jlo, nj, p_lo)) continue;
-            const uint32_t dcol = dstage + plane_slot<DT>(p_lo, dil) * COUT;
-            const uint32_t idesc = nj == 3 ? idesc3 : (nj == 2 ? idesc2 : idesc1);
-            mbar_wait(full_bar(st), ph);
-            tc_fence_after();
-            const uint64_t abase = umma_desc(s_addr + st * a.stage_bytes, 0, a.a_sbo);
-            const uint64_t bbase = umma_desc(wsm + jlo * COUT * 16, a.b_lbo, 128);
-#pragma unroll 4
-            for (int s = 0; s < nsteps; ++s) {
-              const uint64_t adesc = abase + a.a_delta[s];
-              const uint64_t bdesc = bbase + a.b_delta[s];
-              if (elect_one_sync()) umma_f16(dcol, adesc, bdesc, idesc, 1u);
+          const uint32_t b_lo_slot = b_lo_lbo | (((w_addr + slot * a.wchunk_bytes) & 0x3FFFFu) >> 4);
+          // input planes q_rel in [-dil, DT + dil) that exist in the volume
+          const int q_begin = max(-dil, -t.d0), q_end = min(DT + dil, D - t.d0);
+          for (int q_rel = q_begin; q_rel < q_end; ++q_rel) {
+            // kd block j (j = 0,1,2) of this input plane feeds output plane q_rel + (j-1)*dil; the valid ones are contiguous
+            int jlo = 0, nj = 1, p_lo = q_rel;
+            if (nkd == 3) {
+              const int p0 = q_rel - dil, p2 = q_rel + dil;
+              jlo = (p0 < 0) + (q_rel < 0);                                   // p2 >= 0 always holds here
+              nj = (p0 < dteff) + (q_rel < dteff) + (p2 < dteff) - jlo;
+              p_lo = q_rel + (jlo - 1) * dil;
+            } else if (q_rel >= dteff) {
+              nj = 0;
             }
-            if (elect_one_sync()) umma_commit(empty_bar(st));  // frees the activation stage when these MMAs retire
-            __syncwarp();
-            if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
+            if (nj <= 0) continue;
+            const uint32_t dcol = dstage + plane_slot<DT>(p_lo, dil) * COUT;
+            const uint32_t idesc = idesc1 + (uint32_t)(nj - 1) * kIdescNStep;
+            mbar_wait(fbar, ph);
+            tc_fence_after();
+            uint32_t b_lo = b_lo_slot + (uint32_t)(jlo * COUT);
+            if (regular) {
+              if (ntap == 3) {
+                // (an if-chain, not a switch: a jump table would leave the uniform datapath)
+                if (jmode == 1) issue_taps3<1>(dcol, a_lo_st, a_hi, b_lo, b_hi, idesc, kh_step, kw_step, j_step, b_step, 1);
+                else if (jmode & 2) issue_taps3<2>(dcol, a_lo_st, a_hi, b_lo, b_hi, idesc, kh_step, kw_step, j_step, b_step, 2);
+                else if (jmode & 4) issue_taps3<4>(dcol, a_lo_st, a_hi, b_lo, b_hi, idesc, kh_step, kw_step, j_step, b_step, 4);
+                else issue_taps3<0>(dcol, a_lo_st, a_hi, b_lo, b_hi, idesc, kh_step, kw_step, j_step, b_step, jsteps);
+              } else {
+                uint32_t a_lo = a_lo_st;
+#pragma unroll 1
+                for (int j = 0; j < jsteps; ++j) {
+                  if (elect_one_sync()) umma_f16_lohi(dcol, a_lo, a_hi, b_lo, b_hi, idesc);
+                  a_lo += j_step; b_lo += b_step;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int s = 0; s < 5; ++s) {   // paired taps (Cin = 8): always 5 steps
+                const uint2 dl = a.dlt[s];
+                if (elect_one_sync()) umma_f16_lohi(dcol, a_lo_st + dl.x, a_hi, b_lo + dl.y, b_hi, idesc);
+              }
+            }
+            if (elect_one_sync()) umma_commit(fbar + 8u * kConvMaxStages);  // frees the activation stage when these MMAs retire
+            a_lo_st += stage16; fbar += 8u;
+            if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; a_lo_st = a_lo_first; fbar = full_bar(0); }
           }
           if (!resident) {
             if (elect_one_sync()) umma_commit(wempty_bar(slot));
-            __syncwarp();
             ++wcount;
           }
         }
         if (elect_one_sync()) umma_commit(tfull_bar(acc));
-        __syncwarp();
         acc ^= 1u;
         if (acc == 0) accph ^= 1u;
       }
+      __syncwarp();
     }
   } else {
     // =================================== epilogue (4 warps) ===================================
@@ -365,7 +432,16 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, uint16_t* __restri
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-static constexpr uint32_t kSmemBudget = 222u * 1024u;  // + 2 KB static smem (s_run) + alignment slack <= 227 KB
+static constexpr uint32_t kSmemBudgetMax = 222u * 1024u;  // + 2 KB static smem (s_run) + alignment slack <= 227 KB
+static uint32_t smem_budget() {   // SEUNET_CONV_SMEM_KB: experiment knob (leave room for co-resident streaming kernels)
+  static const uint32_t v = [] {
+    const char* e = getenv("SEUNET_CONV_SMEM_KB");
+    uint32_t kb = e ? (uint32_t)atoi(e) : 222u;
+    return std::min(kSmemBudgetMax, std::max(64u, kb) * 1024u);
+  }();
+  return v;
+}
+#define kSmemBudget smem_budget()
 static constexpr uint32_t kBarBytes = 8u * (2 * kConvMaxStages + 32) + 128u;   // barriers + the 128-byte zero block
 
 int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil, int bf16) {
@@ -503,20 +579,28 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
   a.accum_out = accum_out;
   a.out_real_chunks = out_real_chunks < 0 ? g.COUT / 8 : out_real_chunks;
   const uint32_t a_lbo = (uint32_t)HV * 16u;
-  for (int s = 0; s < g.nsteps; ++s) {
-    const PackStep& ps = g.psteps[s];
-    auto tapoff = [&](int t) { return (uint32_t)(((t / 3) * g.dil * lineW + (t % 3) * g.dil) * 16); };
-    ConvStep& cs = a.steps[s];
-    if (g.paired) {
-      cs.a_off = tapoff(ps.tap_a);
-      cs.a_lbo = ps.tap_b >= 0 ? tapoff(ps.tap_b) - tapoff(ps.tap_a) : 16u;
-    } else {
-      cs.a_off = (g.ksize == 3 ? tapoff(ps.tap_a) : 0u) + (uint32_t)(ps.cbase_a / 8) * a_lbo;
-      cs.a_lbo = a_lbo;
+  auto tapoff = [&](int t) { return (uint32_t)(((t / 3) * g.dil * lineW + (t % 3) * g.dil) * 16); };
+  a.a_hi = (((a.a_sbo >> 4) & 0x3FFFu)) | (1u << 14);   // SBO | descriptor version (bit 46)
+  a.b_hi = ((128u >> 4) & 0x3FFFu) | (1u << 14);
+  a.stage16 = a.stage_bytes >> 4;
+  a.b_step = (uint32_t)(2 * nkd * g.COUT);   // one step of the packed weight image = 2 K halves x nkd x COUT rows of 16 B
+  if (g.paired) {
+    if (g.nsteps != 5 || g.nsteps > kConvTableSteps) { seunet_set_error("conv: paired schedule must have 5 steps"); return 1; }
+    a.regular = 0; a.a_lo0 = 0;
+    for (int s = 0; s < g.nsteps; ++s) {
+      const PackStep& ps = g.psteps[s];
+      const uint32_t off = tapoff(ps.tap_a);
+      const uint32_t lbo = ps.tap_b >= 0 ? tapoff(ps.tap_b) - tapoff(ps.tap_a) : 16u;
+      a.dlt[s] = make_uint2((off >> 4) | ((lbo >> 4) << 16), (uint32_t)s * a.b_step);
     }
-    cs.b_off = (uint32_t)s * 2u * nkd * g.COUT * 16u;
-    a.a_delta[s] = (uint64_t)(cs.a_off >> 4) | ((uint64_t)(cs.a_lbo >> 4) << 16);
-    a.b_delta[s] = (uint64_t)(cs.b_off >> 4);
+  } else {
+    // steps are ordered tap-major, 16-channel block minor (conv_geom_init), weights packed in the same order
+    a.regular = 1; a.a_lo0 = ((a_lbo >> 4) & 0x3FFFu) << 16;
+    a.ntap = g.ksize == 3 ? 3 : 1;
+    a.jsteps = g.KC / 16;
+    a.kh_step = (uint32_t)(g.dil * lineW); a.kw_step = (uint32_t)g.dil;
+    a.j_step = 2u * (a_lbo >> 4);
+    if (g.nsteps != (g.ksize == 3 ? 9 : 1) * a.jsteps) { seunet_set_error("conv: step schedule mismatch"); return 1; }
   }
   if (in_chunk_off + g.Cin / 8 > in_chunks_total) { seunet_set_error("conv: input slice exceeds buffer"); return 1; }
   if (out_chunk_off + a.out_real_chunks > out_chunks_total) { seunet_set_error("conv: output slice exceeds buffer"); return 1; }

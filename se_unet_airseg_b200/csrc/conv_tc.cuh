@@ -6,16 +6,10 @@
 constexpr int kConvThreads = 192;   // warp 0: TMA producer, warp 1: UMMA issuer, warps 2-5: epilogue
 constexpr int kConvMaxStages = 32;  // activation stage ring (mbarrier slots)
 constexpr int kConvMaxSteps = 40;   // UMMA K=16 steps per (input plane, channel chunk)
+constexpr int kConvTableSteps = 8;  // steps of the table-driven issue mode (Cin = 8 layers: 5)
 constexpr int kConvTileH = 16;      // one UMMA M=128 block = 16 (h) x 8 (w) voxels of one d-plane
 constexpr int kConvTileW = 8;
 constexpr int kConvAccCols = 256;   // TMEM columns per accumulator stage (2 stages = 512)
-
-struct ConvStep {
-  uint32_t a_off;   // byte offset of the A (activation) start address inside a stage
-  uint32_t a_lbo;   // byte distance between the two 8-channel K halves of this step
-  uint32_t b_off;   // byte offset of the step's weight block inside a weight chunk
-  uint32_t pad;
-};
 
 // Kernel arguments (passed by value as a __grid_constant__).
 struct ConvKArgs {
@@ -38,9 +32,16 @@ struct ConvKArgs {
   const uint8_t* wimg;   // packed weights: [chunk][step][khalf][nkd*COUT rows][8]
   void* out;             // conv output, chunk-plane layout (16-bit elements)
   double* stats;         // [N][COUT][2] running (sum, sum of squares), fp64 atomics
-  ConvStep steps[kConvMaxSteps];
-  uint64_t a_delta[kConvMaxSteps];   // per-step additive delta of the A smem descriptor (addr | lbo<<16)
-  uint64_t b_delta[kConvMaxSteps];   // per-step additive delta of the B smem descriptor
+  // UMMA issue schedule.  Descriptor low words are (start address >> 4) | (LBO >> 4) << 16; the high words are constant.
+  uint32_t a_lo0;        // LBO field of the A descriptor (address part added per stage)
+  uint32_t a_hi, b_hi;   // SBO | version
+  uint32_t stage16;      // stage_bytes >> 4
+  int regular;           // 1: steps follow the (kh, kw, 16-channel block) nest below; 0: use the dlt table
+  int ntap;              // regular: 3 (3x3 in-plane taps) or 1 (pointwise)
+  int jsteps;            // regular: K=16 steps per tap (KC / 16)
+  uint32_t kh_step, kw_step, j_step;   // regular: A start-address increments (16-byte units)
+  uint32_t b_step;       // B start-address increment per step (16-byte units)
+  uint2 dlt[kConvTableSteps];   // table mode (paired taps): per-step {A low-word delta, B low-word delta}
 };
 
 // How the fp32 reference weights map into one UMMA K=16 step of the packed image.

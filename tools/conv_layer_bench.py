@@ -18,7 +18,7 @@ sdt = torch.float16 if L.seunet_act_dtype() == 0 else torch.bfloat16
 st = _lib.stream_ptr()
 tot = 0.0
 for name, cin, cout, k, dil, lvl in LAYERS:
-    if flt and flt not in name:
+    if flt and name not in flt.split(","):
         continue
     s = S >> lvl
     COUT = 16 if cout <= 16 else (32 if cout <= 32 else 64)
@@ -31,11 +31,11 @@ for name, cin, cout, k, dil, lvl in LAYERS:
     scratch = torch.empty(L.seunet_conv_scratch_bytes(cin, cout, k, dil), dtype=torch.uint8, device=dev)
     run = lambda: _lib.check(L.seunet_conv_fprop(_lib.ptr(xin), chunks, 0, _lib.ptr(w), B, s, s, s, cin, cout, k, dil,
                                                  _lib.ptr(out), _lib.ptr(stats), _lib.ptr(scratch), 0, 0, 0, 0, st), "conv")
-    for _ in range(2):
+    for _ in range(int(os.environ.get("CONV_BENCH_WARMUP", "2"))):
         run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    it = 5
+    it = int(os.environ.get("CONV_BENCH_ITERS", "5"))
     e0.record()
     for _ in range(it):
         run()
