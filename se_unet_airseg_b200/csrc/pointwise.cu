@@ -106,7 +106,7 @@ int launch_input_prep(const float* x, const long long* xs, const XOffsets& xo, i
 // =============================================================================================
 template <int C, int GATES>
 __global__ void __launch_bounds__(256) apply_sse_kernel(const __grid_constant__ SseArgs a) {
-  __shared__ float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
+  __shared__ __align__(16) float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double s = a.stats[((size_t)n * a.stats_c + c) * 2], q = a.stats[((size_t)n * a.stats_c + c) * 2 + 1];
@@ -122,34 +122,51 @@ __global__ void __launch_bounds__(256) apply_sse_kernel(const __grid_constant__ 
   __syncthreads();
   const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (v >= a.V) return;
+  // per-channel constants come from shared memory as broadcast 128-bit loads (the kernel is issue-bound otherwise)
+  auto ld8 = [](const float* sm, int k, float* r) {
+    *reinterpret_cast<float4*>(r) = *reinterpret_cast<const float4*>(sm + k * 8);
+    *reinterpret_cast<float4*>(r + 4) = *reinterpret_cast<const float4*>(sm + k * 8 + 4);
+  };
+  float* tp = a.T + (size_t)n * a.V + v;
+  const float t_old = a.t_init ? 0.f : *tp;   // issued with the raw loads, not after the gate arithmetic
   float e[C];
   float g1 = 0.f;
+  Chunk8 in[C / 8];
+#pragma unroll
+  for (int k = 0; k < C / 8; ++k) in[k] = ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8);
 #pragma unroll
   for (int k = 0; k < C / 8; ++k) {
-    float f[8];
-    chunk_to_floats(ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8), f);
+    float f[8], mean[8], rstd[8], wse[8];
+    chunk_to_floats(in[k], f);
+    ld8(s_mean, k, mean); ld8(s_rstd, k, rstd); ld8(s_wse, k, wse);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int c = k * 8 + i;
-      const float t = lrelu_((f[i] - s_mean[c]) * s_rstd[c]);
-      e[c] = t;
-      g1 = fmaf(s_wse[c], t, g1);
+      const float t = lrelu_((f[i] - mean[i]) * rstd[i]);
+      e[k * 8 + i] = t;
+      g1 = fmaf(wse[i], t, g1);
     }
   }
   g1 = sigmoidf_(g1);
-  float g2 = 0.f;
-#pragma unroll
-  for (int c = 0; c < C; ++c) { e[c] *= g1; g2 = fmaf(s_wse2[c], e[c], g2); }
   if (GATES == 2) {
-    g2 = sigmoidf_(g2);
+    float g2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < C; ++c) e[c] *= g2;
+    for (int k = 0; k < C / 8; ++k) {
+      float wse2[8];
+      ld8(s_wse2, k, wse2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { e[k * 8 + i] *= g1; g2 = fmaf(wse2[i], e[k * 8 + i], g2); }
+    }
+    g1 = sigmoidf_(g2);   // the second gate multiplies below
   }
   float t = a.wcst[n];
 #pragma unroll
-  for (int c = 0; c < C; ++c) t = fmaf(s_weff[c], e[c], t);
-  float* tp = a.T + (size_t)n * a.V + v;
-  *tp = a.t_init ? t : (*tp + t);
+  for (int k = 0; k < C / 8; ++k) {
+    float weff[8];
+    ld8(s_weff, k, weff);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { e[k * 8 + i] *= g1; t = fmaf(weff[i], e[k * 8 + i], t); }
+  }
+  *tp = t_old + t;
   if (a.dest) {
 #pragma unroll
     for (int k = 0; k < C / 8; ++k)
@@ -180,87 +197,107 @@ int launch_apply_sse(int C, int N, const SseArgs& a, cudaStream_t st) {
 // CAT block apply:  out = lrelu(IN(y)) [+ lrelu(IN(Wx x))]  -> full-res slot and/or 2x2x2 max-pool
 // (SE_UNet.py:45-49, 186-189, 195-198, 204-206, 212, 218, 224)
 // =============================================================================================
+// One thread owns one (h, w) position of a d-plane (POOL: the 2 x 2 (d, h) voxels of a pooling window at one w) and loops
+// over all channel chunks: index arithmetic, the x-branch loads and the per-channel constants are amortised over C
+// channels, every load/store is a coalesced 16 B per lane, and the w pair of the pooling window is reduced with a shuffle.
 template <int C, bool HASX, bool POOL>
 __global__ void __launch_bounds__(256) apply_cat_kernel(const __grid_constant__ CatArgs a) {
-  __shared__ float s_mean[8], s_rstd[8], s_mx[8], s_rx[8], s_wx[8][kMaxInCh];
-  const int n = blockIdx.z, k = blockIdx.y;
+  __shared__ __align__(16) float s_mean[C], s_rstd[C], s_ax[C], s_bx[C], s_cx[C];
+  const int n = blockIdx.z;
+  const int W = a.d.W, H = a.d.H;
   const long long V = dims_vox(a.d);
-  if (threadIdx.x < 8) {
-    const int c = k * 8 + threadIdx.x;
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
     const double s = a.stats[((size_t)n * a.stats_c + c) * 2], q = a.stats[((size_t)n * a.stats_c + c) * 2 + 1];
     const double mean = s / (double)V;
     double var = q / (double)V - mean * mean;
     if (var < 0) var = 0;
-    s_mean[threadIdx.x] = (float)mean;
-    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)kInEps));
+    s_mean[c] = (float)mean;
+    s_rstd[c] = (float)(1.0 / sqrt(var + (double)kInEps));
     if (HASX) {
-      // analytic InstanceNorm statistics of the 1x1x1 conv of x: mean' = w.mu, var' = w^T Cov w
+      // analytic InstanceNorm statistics of the 1x1x1 conv of x: mean' = w.mu, var' = w^T Cov w;
+      // (w.x - mean') * rstd' is folded into one affine form ax*x0 + bx*x1 + cx
       const double* m = a.mom + (size_t)n * kMomStride;
       const double mu0 = m[0] / V, mu1 = m[1] / V;
       const double c00 = m[2] / V - mu0 * mu0, c11 = m[3] / V - mu1 * mu1, c01 = m[4] / V - mu0 * mu1;
       const double w0 = a.wx[c * a.in_ch], w1 = a.in_ch > 1 ? a.wx[c * a.in_ch + 1] : 0.0;
       double vx = w0 * w0 * c00 + w1 * w1 * c11 + 2.0 * w0 * w1 * c01;
       if (vx < 0) vx = 0;
-      s_mx[threadIdx.x] = (float)(w0 * mu0 + w1 * mu1);
-      s_rx[threadIdx.x] = (float)(1.0 / sqrt(vx + (double)kInEps));
-      s_wx[threadIdx.x][0] = (float)w0;
-      s_wx[threadIdx.x][1] = (float)w1;
+      const double rx = 1.0 / sqrt(vx + (double)kInEps);
+      s_ax[c] = (float)(w0 * rx); s_bx[c] = (float)(w1 * rx); s_cx[c] = (float)(-(w0 * mu0 + w1 * mu1) * rx);
     }
   }
   __syncthreads();
-  const act_t* rawp = a.raw + ((size_t)n * a.raw_chunks + k) * V * 8;
-  auto eval = [&](long long v, int dz, int hy, int wx, float* o) {
-    float f[8];
-    chunk_to_floats(ld_chunk_stream(rawp + (size_t)v * 8), f);
-    float x0 = 0.f, x1 = 0.f;
+  constexpr int NV = POOL ? 4 : 1;
+  const int rows = POOL ? (H >> 1) : H;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = t < rows * W;
+  const int tt = live ? t : 0;
+  const int wx = tt % W, r = tt / W;
+  int vox[NV];
+  float x0[NV], x1[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int dz = POOL ? (int)blockIdx.y * 2 + (j >> 1) : (int)blockIdx.y;
+    const int hy = POOL ? r * 2 + (j & 1) : r;
+    vox[j] = (dz * H + hy) * W + wx;
+    x0[j] = 0.f; x1[j] = 0.f;
     if (HASX) {
       const float* xp = a.x + (a.xo.use ? a.xo.off[n] : n * a.xs[0]) + dz * a.xs[2] + hy * a.xs[3] + wx * a.xs[4];
-      x0 = xp[0];
-      if (a.in_ch > 1) x1 = xp[a.xs[1]];
+      x0[j] = __ldg(xp);
+      if (a.in_ch > 1) x1[j] = __ldg(xp + a.xs[1]);
     }
+  }
+  const int Hp = H >> 1, Wp = W >> 1;
+  const long long Vp = V >> 3;
+  const int pvox = POOL ? ((int)blockIdx.y * Hp + r) * Wp + (wx >> 1) : 0;
+#pragma unroll 1
+  for (int k = 0; k < C / 8; ++k) {
+    const act_t* rawp = a.raw + ((size_t)n * a.raw_chunks + k) * V * 8;
+    float mean[8], rstd[8], ax[8], bx[8], cx[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float r = lrelu_((f[i] - s_mean[i]) * s_rstd[i]);
-      if (HASX) r += lrelu_((fmaf(s_wx[i][0], x0, s_wx[i][1] * x1) - s_mx[i]) * s_rx[i]);
-      o[i] = r;
+    for (int i = 0; i < 8; i += 4) {
+      *reinterpret_cast<float4*>(mean + i) = *reinterpret_cast<const float4*>(s_mean + k * 8 + i);
+      *reinterpret_cast<float4*>(rstd + i) = *reinterpret_cast<const float4*>(s_rstd + k * 8 + i);
+      if (HASX) {
+        *reinterpret_cast<float4*>(ax + i) = *reinterpret_cast<const float4*>(s_ax + k * 8 + i);
+        *reinterpret_cast<float4*>(bx + i) = *reinterpret_cast<const float4*>(s_bx + k * 8 + i);
+        *reinterpret_cast<float4*>(cx + i) = *reinterpret_cast<const float4*>(s_cx + k * 8 + i);
+      }
     }
-  };
-  if (!POOL) {
-    const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (v >= V) return;
-    const int wx = (int)(v % a.d.W), hy = (int)((v / a.d.W) % a.d.H), dz = (int)(v / ((long long)a.d.W * a.d.H));
-    float o[8];
-    eval(v, dz, hy, wx, o);
-    if (a.dest) st_chunk(a.dest + (((size_t)n * a.dest_chunks + a.dest_off + k) * V + v) * 8, floats_to_chunk(o));
-  } else {
-    const int Dp = a.d.D >> 1, Hp = a.d.H >> 1, Wp = a.d.W >> 1;
-    const long long Vp = (long long)Dp * Hp * Wp;
-    const long long pv = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (pv >= Vp) return;
-    const int pw = (int)(pv % Wp), ph = (int)((pv / Wp) % Hp), pd = (int)(pv / ((long long)Wp * Hp));
+    Chunk8 in[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) in[j] = ld_chunk_stream(rawp + (size_t)vox[j] * 8);
     float mx[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) mx[i] = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int dz = pd * 2 + (j >> 2), hy = ph * 2 + ((j >> 1) & 1), wx = pw * 2 + (j & 1);
-      const long long v = ((long long)dz * a.d.H + hy) * a.d.W + wx;
-      float o[8];
-      eval(v, dz, hy, wx, o);
-      if (a.dest) st_chunk(a.dest + (((size_t)n * a.dest_chunks + a.dest_off + k) * V + v) * 8, floats_to_chunk(o));
+    for (int j = 0; j < NV; ++j) {
+      float f[8], o[8];
+      chunk_to_floats(in[j], f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], o[i]);
+      for (int i = 0; i < 8; ++i) {
+        float v = lrelu_((f[i] - mean[i]) * rstd[i]);
+        if (HASX) v += lrelu_(fmaf(ax[i], x0[j], fmaf(bx[i], x1[j], cx[i])));
+        o[i] = v;
+        mx[i] = fmaxf(mx[i], v);
+      }
+      if (a.dest && live) st_chunk(a.dest + (((size_t)n * a.dest_chunks + a.dest_off + k) * V + vox[j]) * 8, floats_to_chunk(o));
     }
-    st_chunk(a.pdest + (((size_t)n * a.pdest_chunks + a.pdest_off + k) * Vp + pv) * 8, floats_to_chunk(mx));
+    if (POOL) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+      if (live && !(wx & 1))
+        st_chunk(a.pdest + (((size_t)n * a.pdest_chunks + a.pdest_off + k) * Vp + pvox) * 8, floats_to_chunk(mx));
+    }
   }
 }
 
 template <int C>
 static int launch_apply_cat_c(const CatArgs& a, cudaStream_t st) {
-  const long long V = dims_vox(a.d);
   const bool pool = a.pdest != nullptr, hasx = a.x != nullptr;
-  const long long items = pool ? V / 8 : V;
-  dim3 grid((unsigned)((items + 255) / 256), C / 8, a.d.N);
+  const int rows = pool ? a.d.H / 2 : a.d.H, planes = pool ? a.d.D / 2 : a.d.D;
+  dim3 grid((unsigned)((rows * a.d.W + 255) / 256), planes, a.d.N);
   if (hasx && pool) apply_cat_kernel<C, true, true><<<grid, 256, 0, st>>>(a);
   else if (hasx) apply_cat_kernel<C, true, false><<<grid, 256, 0, st>>>(a);
   else if (pool) apply_cat_kernel<C, false, true><<<grid, 256, 0, st>>>(a);
