@@ -66,54 +66,81 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   const int x_chunk = a.x_chunk_off + (a.ksize == 3 ? 0 : pass * 16);
   const int dshift = (kd - 1) * a.dil, hshift = (kh - 1) * a.dil;
 
-  auto decode = [&](int tp, int& n, int& p, int& h0, int& w0) {
-    w0 = (tp % a.tilesW) * 8; tp /= a.tilesW;
-    h0 = (tp % a.tilesH) * 16; tp /= a.tilesH;
-    p = tp % a.D; n = tp / a.D;
+  // Each CTA of a pass walks a CONTIGUOUS range of tile planes; the (w, h, plane, sample) coordinates are advanced with
+  // carries - the single-thread producer and issuer loops are issue-bound, and four runtime integer divisions per tile
+  // cost more than the eight MMAs they feed.
+  const int tp_begin = (int)((long long)rank * a.numTilePlanes / a.ctas_per_pass);
+  const int tp_end = (int)((long long)(rank + 1) * a.numTilePlanes / a.ctas_per_pass);
+  struct Walk { int tw, th, p, n; };
+  auto walk_init = [&](int tp) {
+    Walk w;
+    w.tw = tp % a.tilesW; tp /= a.tilesW;
+    w.th = tp % a.tilesH; tp /= a.tilesH;
+    w.p = tp % a.D; w.n = tp / a.D;
+    return w;
+  };
+  auto walk_next = [&](Walk& w) {
+    if (++w.tw == a.tilesW) { w.tw = 0; if (++w.th == a.tilesH) { w.th = 0; if (++w.p == a.D) { w.p = 0; ++w.n; } } }
   };
 
   if (warp == 0) {
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
-      for (int tp = rank; tp < a.numTilePlanes; tp += a.ctas_per_pass) {
-        int n, p, h0, w0;
-        decode(tp, n, p, h0, w0);
+      Walk w = walk_init(tp_begin);
+      const uint32_t tx_bytes = a.x_box_bytes + ntap * a.dy_box_bytes;
+      const int kw0 = ntap == 3 ? 1 : 0;
+      for (int tp = tp_begin; tp < tp_end; ++tp, walk_next(w)) {
         // tile plane `p` indexes the INPUT plane; it pairs with output-gradient plane p - dshift
-        const int po = p - dshift;
+        const int po = w.p - dshift;
         if (po < 0 || po >= a.D) continue;
+        const int w0 = w.tw * a.tw, h0 = w.th * 16;
         mbar_wait(empty_bar(st), ph ^ 1u);
-        mbar_expect_tx(full_bar(st), a.x_box_bytes + ntap * a.dy_box_bytes);
-        tma_load_4d(x_addr + st * a.x_stage_bytes, &tmap_x, full_bar(st), 8 * w0, h0, p, n * a.x_chunks_total + x_chunk);
+        mbar_expect_tx(full_bar(st), tx_bytes);
+        tma_load_4d(x_addr + st * a.x_stage_bytes, &tmap_x, full_bar(st), 8 * w0, h0, w.p, w.n * a.x_chunks_total + x_chunk);
         for (int kw = 0; kw < ntap; ++kw)   // dY shifted against the taps: X[u] pairs with dY[u - shift(kd,kh,kw)]
           tma_load_4d(dy_addr + st * a.dy_stage_bytes + kw * a.dy_box_bytes, &tmap_dy, full_bar(st),
-                      8 * (w0 - (kw - (ntap == 3 ? 1 : 0)) * a.dil), h0 - hshift, po, n * a.dy_chunks_total + a.dy_chunk_off);
+                      8 * (w0 - (kw - kw0) * a.dil), h0 - hshift, po, w.n * a.dy_chunks_total + a.dy_chunk_off);
         if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     uint32_t st = 0, ph = 0, any = 0;
     const uint32_t idesc = umma_idesc2(a.fmt_a, a.fmt_b, 1u, 1u, a.m64 ? 64 : 128, ntap * COUT);
-    for (int tp = rank; tp < a.numTilePlanes; tp += a.ctas_per_pass) {
-      int n, p, h0, w0;
-      decode(tp, n, p, h0, w0);
+    // A (X tile, 16x8 voxels, no halo) and B (ntap shifted dY tiles stacked along N): MN-major, m/n-groups = chunk planes
+    // 2048 B apart (SBO), k-groups = h lines 128 B apart (LBO).  Only the low descriptor word (address) changes.
+    const uint32_t desc_hi = ((a.x_plane_bytes >> 4) & 0x3FFFu) | (1u << 14);   // SBO = chunk-plane stride (16 x tw voxels)
+    const int ksteps = a.tw;   // K=16 steps per tile plane
+    const uint32_t lbo_bits = ((128u >> 4) & 0x3FFFu) << 16;
+    const uint32_t a_lo_first = lbo_bits | ((x_addr & 0x3FFFFu) >> 4), b_lo_first = lbo_bits | ((dy_addr & 0x3FFFFu) >> 4);
+    const uint32_t a_stage16 = a.x_stage_bytes >> 4, b_stage16 = a.dy_stage_bytes >> 4;
+    uint32_t a_lo_st = a_lo_first, b_lo_st = b_lo_first, fbar = full_bar(0);
+    int p = walk_init(tp_begin).p, tw = walk_init(tp_begin).tw, th = walk_init(tp_begin).th;
+    for (int tp = tp_begin; tp < tp_end; ++tp) {
       const int po = p - dshift;
+      if (++tw == a.tilesW) { tw = 0; if (++th == a.tilesH) { th = 0; if (++p == a.D) p = 0; } }
       if (po < 0 || po >= a.D) continue;
-      mbar_wait(full_bar(st), ph);
+      mbar_wait(fbar, ph);
       tc_fence_after();
-      // A (X tile, 16x8 voxels, no halo) and B (ntap shifted dY tiles stacked along N): MN-major, m/n-groups = chunk planes
-      // 2048 B apart (SBO), k-groups = h lines 128 B apart (LBO)
-      uint64_t adesc = umma_desc(x_addr + st * a.x_stage_bytes, 128u, 2048u);
-      uint64_t bdesc = umma_desc(dy_addr + st * a.dy_stage_bytes, 128u, 2048u);
+      if (!any) {   // first tile plane of this CTA: the first MMA overwrites the accumulators
+        if (elect_one_sync()) {
+          const uint64_t ad = ((uint64_t)desc_hi << 32) | a_lo_st, bd = ((uint64_t)desc_hi << 32) | b_lo_st;
+          umma_f16(tmem_base, ad, bd, idesc, 0u);
+        }
+        any = 1;
+#pragma unroll 1
+        for (int j = 1; j < ksteps; ++j)
+          if (elect_one_sync()) umma_f16_lohi(tmem_base, a_lo_st + 16u * j, desc_hi, b_lo_st + 16u * j, desc_hi, idesc);
+      } else {
+#pragma unroll 1
+        for (int j8 = 0; j8 < ksteps; j8 += 8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (elect_one_sync()) umma_f16(tmem_base, adesc, bdesc, idesc, (any | (uint32_t)j) != 0u ? 1u : 0u);
-        adesc += 16u;   // two h lines = 256 B
-        bdesc += 16u;
+          for (int j = 0; j < 8; ++j)   // two h-line segments of 8 voxels = 256 B per K=16 step
+            if (elect_one_sync()) umma_f16_lohi(tmem_base, a_lo_st + 16u * (j8 + j), desc_hi, b_lo_st + 16u * (j8 + j), desc_hi, idesc);
+        }
       }
-      any = 1;
-      if (elect_one_sync()) umma_commit(empty_bar(st));
-      __syncwarp();
-      if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
+      if (elect_one_sync()) umma_commit(fbar + 64u);   // empty barrier of this stage
+      a_lo_st += a_stage16; b_lo_st += b_stage16; fbar += 8u;
+      if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; a_lo_st = a_lo_first; b_lo_st = b_lo_first; fbar = full_bar(0); }
     }
     if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(count_addr), "r"(any) : "memory");
     __syncwarp();
@@ -206,7 +233,19 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   const int halo = ksize == 3 ? dil : 0;
   const int npass = ksize == 3 ? 9 : (Cin + 127) / 128;
   a.N = N; a.D = D; a.H = H; a.W = W;
-  a.tilesW = (W + 7) / 8; a.tilesH = (H + 15) / 16;
+  // Tile width: the per-stage costs (4 TMA instructions, barrier round trip, loop bookkeeping of the single-thread
+  // producer/issuer) dominate narrow layers, so a stage covers as many voxels as ~100 KB of shared memory allow
+  // (two stages of 80 KB measured faster than five of 40 KB).
+  {
+    const int coutp = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : 64);
+    const int xpl = std::min(16, (Cin + 7) / 8);
+    const uint32_t per8 = 2048u * xpl + (ksize == 3 ? 3u : 1u) * 2048u * (coutp / 8);   // stage bytes at tw = 8
+    int tw = 8;
+    static const uint32_t cap_kb = getenv("SEUNET_WG_STAGE_KB") ? (uint32_t)atoi(getenv("SEUNET_WG_STAGE_KB")) : 100u;
+    while (tw < 32 && per8 * (tw * 2 / 8) <= cap_kb * 1024u && W >= tw * 2) tw *= 2;
+    a.tw = tw;
+  }
+  a.tilesW = (W + a.tw - 1) / a.tw; a.tilesH = (H + 15) / 16;
   a.numTilePlanes = N * D * a.tilesH * a.tilesW;
   a.dil = halo; a.ksize = ksize;
   a.lineW = 8 + 2 * halo;
@@ -217,10 +256,10 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   const int xplanes = std::min(16, cin_planes_total);
   a.x_chunks_total = x_chunks_total; a.x_chunk_off = x_chunk_off;
   a.dy_chunks_total = dy_chunks_total; a.dy_chunk_off = dy_chunk_off;
-  a.x_plane_bytes = 2048u;   // 16 x 8 voxels x 16 B, no halo: the tap shifts are applied to dY
+  a.x_plane_bytes = 256u * a.tw;   // 16 x tw voxels x 16 B, no halo: the tap shifts are applied to dY
   a.x_box_bytes = a.x_plane_bytes * xplanes;
   a.x_stage_bytes = (a.x_box_bytes + 127u) & ~127u;
-  a.dy_box_bytes = 128u * L->COUT * 2u;
+  a.dy_box_bytes = a.x_plane_bytes * (L->COUT / 8);
   a.dy_stage_bytes = (ksize == 3 ? 3u : 1u) * a.dy_box_bytes;
   int nst = (int)((200u * 1024u) / (a.x_stage_bytes + a.dy_stage_bytes));
   nst = std::min(nst, 6);
@@ -245,7 +284,7 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   {
     cuuint64_t gdim[4] = {(cuuint64_t)8 * W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N * x_chunks_total};
     cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-    cuuint32_t box[4] = {64u, 16u, 1u, (cuuint32_t)xplanes};
+    cuuint32_t box[4] = {(cuuint32_t)(8 * a.tw), 16u, 1u, (cuuint32_t)xplanes};
     CUresult r = enc(&L->tmap_x, x_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
                      const_cast<void*>(x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -254,7 +293,7 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   {
     cuuint64_t gdim[4] = {(cuuint64_t)8 * W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N * dy_chunks_total};
     cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-    cuuint32_t box[4] = {64u, 16u, 1u, (cuuint32_t)(L->COUT / 8)};
+    cuuint32_t box[4] = {(cuuint32_t)(8 * a.tw), 16u, 1u, (cuuint32_t)(L->COUT / 8)};
     CUresult r = enc(&L->tmap_dy, x_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(dy), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

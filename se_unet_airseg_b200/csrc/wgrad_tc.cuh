@@ -7,6 +7,7 @@ struct WgradKArgs {
   int N, D, H, W;
   int tilesW, tilesH, numTilePlanes;
   int dil, ksize, lineW;
+  int tw;              // tile width in voxels (8, 16 or 32): one stage = 16 x tw voxels = tw K=16 MMA steps
   int ctas_per_pass, nstages;
   int x_chunks_total, x_chunk_off, dy_chunks_total, dy_chunk_off;
   uint32_t x_plane_bytes, x_box_bytes, x_stage_bytes, dy_box_bytes, dy_stage_bytes, bar_off;
