@@ -33,14 +33,19 @@
 // ---------------------------------------------------------------------------------------------
 // device
 // ---------------------------------------------------------------------------------------------
-struct TileCoord { int n, d0, h0, w0; };
+struct TileCoord { int n, d0, h0, w0, par, Dp; };   // d0 / Dp count planes of the tile's parity class (see ConvKArgs::dstep)
 
 template <int DT>
 __device__ __forceinline__ TileCoord decode_tile(const ConvKArgs& a, int tile) {
   TileCoord t;
   const int tw = tile % a.tilesW; tile /= a.tilesW;
   const int th = tile % a.tilesH; tile /= a.tilesH;
-  const int td = tile % a.tilesD; tile /= a.tilesD;
+  int td = tile % a.tilesD; tile /= a.tilesD;
+  // dstep == 2 (dilation 2): a tile holds DT planes of ONE parity, d = par + 2 * (d0 + i); the kd taps then reach the
+  // neighbouring planes of the same parity class, so a tile needs DT + 2 input planes instead of DT + 4.
+  t.par = 0;
+  if (a.dstep == 2) { const int half = a.tilesD >> 1; t.par = td >= half ? 1 : 0; td -= t.par * half; }
+  t.Dp = a.dstep == 2 ? ((a.D - t.par + 1) >> 1) : a.D;
   t.n = tile; t.d0 = td * DT; t.h0 = th * kConvTileH; t.w0 = tw * kConvTileW;
   return t;
 }
@@ -186,11 +191,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           for (int qi = 0; qi < nq; ++qi) {
             int jlo, nj, p_lo;
             const int q_rel = qi - a.dil;
-            if (!plane_blocks(a.nkd, a.dil, a.D, t.d0, min(DT, a.D - t.d0), q_rel, jlo, nj, p_lo)) continue;
+            if (!plane_blocks(a.nkd, a.dil, t.Dp, t.d0, min(DT, t.Dp - t.d0), q_rel, jlo, nj, p_lo)) continue;
             mbar_wait(empty_bar(st), ph ^ 1u);
             mbar_expect_tx(full_bar(st), a.box_bytes);
             tma_load_4d(s_addr + st * a.stage_bytes, &tmap, full_bar(st),
-                        8 * (t.w0 - a.halo), t.h0 - a.halo, t.d0 + q_rel,
+                        8 * (t.w0 - a.halo), t.h0 - a.halo, t.par + a.dstep * (t.d0 + q_rel),
                         t.n * a.in_chunks_total + a.in_chunk_off + c * a.kc8);
             if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
           }
@@ -207,7 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       constexpr uint32_t kIdescNStep = (uint32_t)(COUT >> 3) << 17;   // one more kd block along N
       const uint32_t idesc_clear = umma_idesc(a.fmt, 128, kConvAccCols);
       const uint64_t zdesc = umma_desc(zero_addr, 0, 0);   // every core matrix reads the same 128 zero bytes
-      const int dil = a.dil, nkd = a.nkd, D = a.D;
+      const int dil = a.dil, nkd = a.nkd;
       const uint32_t a_hi = a.a_hi, b_hi = a.b_hi, stage16 = a.stage16;
       const uint32_t a_lo_first = a.a_lo0 | ((s_addr & 0x3FFFFu) >> 4);
       const uint32_t b_lo_lbo = ((a.b_lbo >> 4) & 0x3FFFu) << 16;
@@ -219,6 +224,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       const uint32_t kh_step = a.kh_step, kw_step = a.kw_step, j_step = a.j_step, b_step = a.b_step;
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<DT>(a, tile);
+        const int D = t.Dp;
         const int dteff = min(DT, D - t.d0);
         mbar_wait(tempty_bar(acc), accph ^ 1u);
         tc_fence_after();
@@ -329,8 +335,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                              ((size_t)h * a.W + w) * 8;   // element offset
 #pragma unroll 1
         for (int s = 0; s < DT; ++s) {
-          const int d = t.d0 + slot_plane<DT>(s, a.dil);
-          if (d >= a.D) continue;  // warp-uniform
+          const int dp = t.d0 + slot_plane<DT>(s, a.dil);
+          if (dp >= t.Dp) continue;  // warp-uniform
+          const int d = t.par + a.dstep * dp;
           uint32_t v[16];
           tmem_ld16(tacc + s * COUT + cg * 16, v);
           tmem_ld_wait();
@@ -559,9 +566,11 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
   a.N = N; a.D = D; a.H = H; a.W = W;
   a.tilesW = (W + kConvTileW - 1) / kConvTileW;
   a.tilesH = (H + kConvTileH - 1) / kConvTileH;
-  a.tilesD = (D + DT - 1) / DT;
+  // dilation 2: split the planes into the two parity classes (plane distance of the kd taps becomes 1 inside a class)
+  a.dstep = (nkd == 3 && g.dil == 2) ? 2 : 1;
+  a.tilesD = a.dstep == 2 ? 2 * (((D + 1) / 2 + DT - 1) / DT) : (D + DT - 1) / DT;
   a.numTiles = a.tilesW * a.tilesH * a.tilesD * N;
-  a.dil = nkd == 3 ? g.dil : 0;
+  a.dil = nkd == 3 ? (a.dstep == 2 ? 1 : g.dil) : 0;
   a.nkd = nkd; a.halo = halo;
   a.nchunks = g.nchunks; a.kc8 = g.KC / 8;
   a.in_chunks_total = in_chunks_total; a.in_chunk_off = in_chunk_off;

@@ -15,7 +15,8 @@ constexpr int kConvAccCols = 256;   // TMEM columns per accumulator stage (2 sta
 struct ConvKArgs {
   int N, D, H, W;
   int tilesW, tilesH, tilesD, numTiles;
-  int dil;            // plane distance of the kd taps (0 when nkd == 1)
+  int dil;            // distance of the kd taps in planes of the tile's parity class (0 when nkd == 1)
+  int dstep;          // 2 for dilation-2 layers: tiles hold planes of one parity (d = par + 2*i); else 1
   int nkd;            // 3: kd taps stacked along UMMA N; 1: pointwise conv
   int halo;           // in-plane halo (dil for 3x3x3, 0 for 1x1x1)
   int nchunks, kc8;   // channel chunks per tile, 8-channel planes per chunk
