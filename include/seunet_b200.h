@@ -157,6 +157,23 @@ int seunet_window_accumulate(const float* logits, const int* starts, int B, int 
 int seunet_window_finalize(float* acc, const int* counts_dev, int X, int Y, int Z, float threshold,
                            unsigned char* mask, int write_mean, seunet_stream_t stream);
 
+/* ---- post-processing of the mean-probability volume (prediction.py:13-37, 111-116; util.py:58-75) ----
+ * scratch: caller-owned DEVICE buffer of seunet_postproc_scratch_bytes(); max_runs bounds the number of row runs (maximal
+ * runs of set voxels along the last axis) the component labelling may see - D*H*ceil(W/2) is always enough. */
+size_t seunet_postproc_scratch_bytes(int D, int H, int W, int64_t max_runs);
+/* double_threshold_iteration(pred, h_thresh, l_thresh) - the reference's single in-place raster sweep, bit-exact - then
+ * (border_frac >= 0) zeroing of the first/last int(border_frac*n) planes of axes 0 and 1 (prediction.py:112-115).
+ * The bit-packed result stays in scratch for seunet_postproc_largest_component; mask_out (uint8 [D][H][W]) may be NULL. */
+int seunet_postproc_dti(const float* prob, int D, int H, int W, double h_thresh, double l_thresh, double border_frac,
+                        unsigned char* mask_out, void* scratch, int64_t max_runs, seunet_stream_t stream);
+/* maximum_3d (util.py:58-75): largest 26-connected component (the second largest when the largest misses the slices
+ * k = W/2, W/3, (W/3)*2 of the last axis), then binary_fill_holes (fill_holes != 0).  mask_in == NULL takes the bitmask left
+ * in scratch by seunet_postproc_dti.  info_out (DEVICE int[16], may be NULL): [0] error (1 = more runs than max_runs),
+ * [1] foreground runs, [2] voxels of the largest component, [3] of the second, [4] 1 if the second was chosen. */
+int seunet_postproc_largest_component(const unsigned char* mask_in, int D, int H, int W, int fill_holes,
+                                      unsigned char* mask_out, int* info_out, void* scratch, int64_t max_runs,
+                                      seunet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

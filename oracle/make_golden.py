@@ -115,5 +115,46 @@ def main():
         print("stage", stage, "loss", loss.item())
 
 
+def load_reference_dti():
+    """prediction.py imports pyvista/skimage/stl (not installed here): only the FunctionDef of double_threshold_iteration
+    is executed, with numpy as its sole global."""
+    src = open(os.path.join(REF, "prediction.py")).read()
+    ns = {"np": np}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == "double_threshold_iteration":
+            exec(compile(ast.Module([node], []), "prediction.py", "exec"), ns)
+    return ns["double_threshold_iteration"]
+
+
+def synth_prob(shape, seed):
+    """Smooth random probability field with strong cores, weak halos and isolated weak specks (float32, like the mean of
+    sigmoid outputs), plus exact threshold values."""
+    rng = np.random.RandomState(seed)
+    from scipy import ndimage
+    f = ndimage.gaussian_filter(rng.rand(*shape), 1.2)
+    f = (f - f.min()) / (f.max() - f.min())
+    p = (0.15 + 0.7 * f + 0.08 * (rng.rand(*shape) - 0.5)).astype(np.float32)
+    flat = p.reshape(-1)
+    flat[rng.randint(0, flat.size, 8)] = np.float32(0.5)
+    flat[rng.randint(0, flat.size, 8)] = np.float32(0.4)
+    return p
+
+
+def main_postproc():
+    dti = load_reference_dti()
+    for shape, seed in (((12, 14, 20), 1), ((9, 16, 37), 2), ((16, 10, 70), 3)):
+        p = synth_prob(shape, seed)
+        ref = dti(p.copy(), h_thresh=0.5, l_thresh=0.4)
+        mine = oracle.double_threshold_iteration(p, 0.5, 0.4)
+        assert np.array_equal(ref, mine), "oracle restatement differs from the reference's double_threshold_iteration"
+        name = "postproc_dti_%dx%dx%d.npz" % shape
+        np.savez_compressed(os.path.join(OUT, name), prob=p, dti=ref.astype(np.uint8), seed=seed)
+        print(name, "set voxels", int(ref.sum()), "strong", int((p >= 0.5).sum()))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "postproc":
+        main_postproc()
+    else:
+        main()
+        main_postproc()

@@ -339,3 +339,55 @@ def predict_volume(sd, img_stored, cube=128, step=64):
                     pred_num[xl:xl + cube, yl:yl + cube, zl:zl + cube] += 1        # :107
     pred = pred / pred_num                                                         # :109
     return pred, (pred >= 0.5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# post-processing - restated from prediction.py:13-37, 111-116 and util.py:58-75
+# ---------------------------------------------------------------------------------------------------------------------
+def double_threshold_iteration(pred, h_thresh, l_thresh):
+    """prediction.py:13-37.  `gbin_pre = gbin` aliases the array, so the reference's while loop performs exactly ONE in-place
+    raster sweep; that visiting-order dependence is part of the behaviour and is kept.  Pure-Python loops: small volumes only."""
+    import numpy as np
+    pred = np.array(np.asarray(pred) * 255, dtype=np.float64)
+    h, w, z = pred.shape
+    gbin = np.where(pred >= h_thresh * 255, 255, 0).astype(np.float64)
+    neigb = [(a, b, c) for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1) if (a, b, c) != (0, 0, 0)]
+    for i in range(h):
+        for j in range(w):
+            for k in range(z):
+                if gbin[i, j, k] == 0 and pred[i, j, k] < h_thresh * 255 and pred[i, j, k] >= l_thresh * 255:
+                    for a, b, c in neigb:
+                        if gbin[max(min(i + a, h - 1), 0), max(min(j + b, w - 1), 0), max(min(k + c, z - 1), 0)]:
+                            gbin[i, j, k] = 255
+                            break
+    return gbin / 255
+
+
+def zero_borders(pred, frac=0.15):
+    """prediction.py:112-115."""
+    pred = pred.copy()
+    pred[0:int(frac * pred.shape[0]), :, :] = 0
+    pred[int((1 - frac) * pred.shape[0]):, :, :] = 0
+    pred[:, 0:int(frac * pred.shape[1]), :] = 0
+    pred[:, int((1 - frac) * pred.shape[1]):, :] = 0
+    return pred
+
+
+def maximum_3d(region01, fill_holes=True):
+    """util.py:58-75 with scipy.ndimage.label (full 3x3x3 structure) in place of cc3d (not installed here): both number the
+    components in raster order of their first voxel, which fixes the tie rule of the reversed stable sort."""
+    import numpy as np
+    from scipy import ndimage
+    label, num = ndimage.label(np.asarray(region01) != 0, structure=np.ones((3, 3, 3)))
+    if num == 0:
+        return np.zeros(region01.shape, dtype=bool)
+    areas = np.bincount(label.ravel(), minlength=num + 1)
+    num_list = list(range(1, num + 1))
+    order = sorted(num_list, key=lambda x: areas[x])[::-1]
+    best = label == order[0]
+    z = region01.shape[2]
+    if not best[:, :, z // 2].any() and not best[:, :, z // 3].any() and not best[:, :, z // 3 * 2].any() and num > 1:
+        best = label == order[1]
+    if fill_holes:
+        best = ndimage.binary_fill_holes(best.astype(np.int8))
+    return best

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libseunet_b200.so")
 STAMP = os.path.join(HERE, ".libseunet_b200.stamp")
-SOURCES = ["conv_tc.cu", "wgrad_tc.cu", "pointwise.cu", "pointwise2.cu", "window.cu", "backward.cu", "backward2.cu", "loss.cu", "plan.cu"]  # missing files are skipped
+SOURCES = ["conv_tc.cu", "wgrad_tc.cu", "pointwise.cu", "pointwise2.cu", "window.cu", "backward.cu", "backward2.cu", "loss.cu", "postproc.cu", "plan.cu"]  # missing files are skipped
 HEADERS = ["common.cuh", "conv_tc.cuh", "wgrad_tc.cuh", "pointwise.cuh", "backward.cuh", os.path.join("..", "..", "include", "seunet_b200.h")]
 
 NVCC_FLAGS = [

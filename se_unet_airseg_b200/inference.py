@@ -131,6 +131,18 @@ class SlidingWindowPredictor:
                                             _lib.ptr(g["mask"]), 1 if return_prob else 0, st), "seunet_window_finalize")
         return (g["mask"], g["acc"]) if return_prob else g["mask"]
 
+    @torch.no_grad()
+    def predict_postprocessed_device(self, img_dev, hu_offset=-1024.0, h_thresh=0.5, l_thresh=0.4, border_frac=0.15):
+        """The whole of prediction.py:78-116 on the device: sliding-window mean probability, double-threshold hysteresis,
+        border crop, largest 26-connected component, hole filling.  Returns the final uint8 mask (X, Y, Z)."""
+        from .postprocess import PostProcessor
+        _, prob = self.predict_device(img_dev, hu_offset, return_prob=True)
+        pp = getattr(self, "_post", None)
+        if pp is None or (pp.D, pp.H, pp.W) != tuple(prob.shape) or pp.device != prob.device:
+            pp = PostProcessor(tuple(prob.shape), prob.device)
+            self._post = pp
+        return pp(prob, h_thresh, l_thresh, border_frac)
+
     def _buffers(self, plan, b, dev):
         buf = getattr(plan, "_sw_buffers", None)
         if buf is None:

@@ -100,3 +100,29 @@ def test_window_enumeration_matches_prediction_py():
         assert window_starts(n) == oracle.window_starts(n)
     c = coverage_counts(400, window_starts(400), 128)
     assert c.min() >= 1 and c[300] == 3
+
+
+def test_oracle_dti_reproduces_reference_golden():
+    """tests/golden/postproc_dti_*.npz: outputs of the reference's own double_threshold_iteration (prediction.py:13-37),
+    extracted with ast by oracle/make_golden.py."""
+    import glob
+    files = sorted(glob.glob(os.path.join(GOLDEN, "postproc_dti_*.npz")))
+    assert files
+    for f in files:
+        z = np.load(f)
+        got = oracle.double_threshold_iteration(z["prob"], 0.5, 0.4)
+        assert np.array_equal(got.astype(np.uint8), z["dti"]), f
+
+
+def test_oracle_maximum_3d_rules():
+    """util.py:58-75 restated with scipy (cc3d is not installed): largest component, probe-slice fallback, hole filling."""
+    m = np.zeros((8, 8, 30), np.uint8)
+    m[1:7, 1:7, 1:7] = 1; m[2:6, 2:6, 2:6] = 0      # hollow box: 152 voxels, misses the probe slices k = 15, 10, 20
+    m[3, 3, 9:22] = 1                               # 13-voxel bar through all three probe slices
+    out = oracle.maximum_3d(m)
+    assert out[3, 3, 9:22].all() and not out[1, 1, 1]          # the second largest component was chosen
+    m2 = m.copy(); m2[3, 3, 9:22] = 0; m2[1:7, 1:7, 14] = 1    # now the box component is alone and the slab touches k = 15 ...
+    out2 = oracle.maximum_3d(m2)
+    assert out2[1:7, 1:7, 14].all()
+    m3 = np.zeros((8, 8, 8), np.uint8); m3[1:7, 1:7, 1:7] = 1; m3[2:6, 2:6, 2:6] = 0
+    assert oracle.maximum_3d(m3)[3, 3, 3] and not oracle.maximum_3d(m3, fill_holes=False)[3, 3, 3]
