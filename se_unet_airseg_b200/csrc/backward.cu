@@ -251,7 +251,7 @@ __device__ __forceinline__ void cat_prologue(const act_t*, const double* stats, 
 }
 
 template <bool HASX, bool POOL>
-__global__ void __launch_bounds__(256) cat_bwd_a_kernel(const __grid_constant__ CatBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) cat_bwd_a_kernel(const __grid_constant__ CatBwdArgs a) {
   __shared__ CatCoef s;
   __shared__ float s_red[8][32];
   __shared__ float s_max[8];
@@ -302,51 +302,73 @@ __global__ void __launch_bounds__(256) cat_bwd_a_kernel(const __grid_constant__ 
       nx[i] = HASX ? (fmaf(s.w0[i], x0, s.w1[i] * x1) - s.mx[i]) * s.rx[i] : 0.f;
     }
   };
+  // blockIdx.x walks d-planes (pooled planes when POOL); a thread owns one (h, w) position of the plane - 32-bit index
+  // arithmetic, fully coalesced 16/32-byte accesses (the 64-bit div/mod per voxel of the first version cost more than
+  // the memory traffic).
+  const int W = a.d.W, H = a.d.H;
   if (!POOL) {
-    for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
-      const int wx = (int)(v % a.d.W), hy = (int)((v / a.d.W) % a.d.H), dz = (int)(v / ((long long)a.d.W * a.d.H));
-      float ny[8], nx[8], G[8];
-      norms(v, dz, hy, wx, ny, nx);
-      ld_grad8(gp_ + (size_t)v * 8, G);
-      accumulate(v, ny, nx, G);
-    }
-  } else {
-    const int Dp = a.d.D >> 1, Hp = a.d.H >> 1, Wp = a.d.W >> 1;
-    const long long Vp = (long long)Dp * Hp * Wp;
-    const grad_t* gpool = a.gp + ((size_t)n * a.gp_chunks + a.gp_off + k) * Vp * 8;
-    for (long long pv = blockIdx.x * (long long)blockDim.x + threadIdx.x; pv < Vp; pv += (long long)gridDim.x * blockDim.x) {
-      const int pw = (int)(pv % Wp), ph = (int)((pv / Wp) % Hp), pd = (int)(pv / ((long long)Wp * Hp));
-      // pass 1: arg-max of the forward output per channel (first maximum in (d,h,w) scan order, like max_pool3d)
-      float best[8];
-      int arg[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; arg[i] = 0; }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int dz = pd * 2 + (j >> 2), hy = ph * 2 + ((j >> 1) & 1), wx = pw * 2 + (j & 1);
-        const long long v = ((long long)dz * a.d.H + hy) * a.d.W + wx;
-        float ny[8], nx[8];
-        norms(v, dz, hy, wx, ny, nx);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float o = lrelu_(ny[i]) + (HASX ? lrelu_(nx[i]) : 0.f);
-          if (o > best[i]) { best[i] = o; arg[i] = j; }
-        }
-      }
-      float GP[8];
-      ld_grad8(gpool + (size_t)pv * 8, GP);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int dz = pd * 2 + (j >> 2), hy = ph * 2 + ((j >> 1) & 1), wx = pw * 2 + (j & 1);
-        const long long v = ((long long)dz * a.d.H + hy) * a.d.W + wx;
+    for (int dz = blockIdx.x; dz < a.d.D; dz += gridDim.x)
+      for (int t = threadIdx.x; t < H * W; t += blockDim.x) {
+        const int hy = t / W, wx = t - hy * W;
+        const long long v = ((long long)dz * H + hy) * W + wx;
         float ny[8], nx[8], G[8];
         norms(v, dz, hy, wx, ny, nx);
         ld_grad8(gp_ + (size_t)v * 8, G);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) G[i] += (arg[i] == j) ? GP[i] : 0.f;
         accumulate(v, ny, nx, G);
       }
-    }
+  } else {
+    // POOL: a thread owns the 2 (d) x 2 (h) voxels of a pooling window at ONE w; the w pair (adjacent lanes, W is even)
+    // settles the arg-max with one shuffle.  Scan index inside the window: J = 4*dd + 2*dh + dw (max_pool3d keeps the first
+    // maximum in (d,h,w) order).
+    const int Dp = a.d.D >> 1, Hp = H >> 1, Wp = W >> 1;
+    const long long Vp = (long long)Dp * Hp * Wp;
+    const grad_t* gpool = a.gp + ((size_t)n * a.gp_chunks + a.gp_off + k) * Vp * 8;
+    const int per_plane = Hp * W, rounded = (per_plane + 31) & ~31;
+    for (int pd = blockIdx.x; pd < Dp; pd += gridDim.x)
+      for (int t = threadIdx.x; t < rounded; t += blockDim.x) {
+        const bool live = t < per_plane;
+        const int tt = live ? t : 0;
+        const int ph = tt / W, wx = tt - ph * W;
+        float best[8];
+        int arg[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; arg[i] = 0; }
+#pragma unroll 1   // (fully unrolled, the two window passes need 252 registers: one block per SM)
+        for (int j = 0; j < 4; ++j) {
+          const int dz = pd * 2 + (j >> 1), hy = ph * 2 + (j & 1);
+          const long long v = ((long long)dz * H + hy) * W + wx;
+          float ny[8], nx[8];
+          norms(v, dz, hy, wx, ny, nx);
+          const int J = (j >> 1) * 4 + (j & 1) * 2 + (wx & 1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float o = lrelu_(ny[i]) + (HASX ? lrelu_(nx[i]) : 0.f);
+            if (o > best[i]) { best[i] = o; arg[i] = J; }
+          }
+        }
+        float GP[8];
+        ld_grad8(gpool + (size_t)(((long long)pd * Hp + ph) * Wp + (wx >> 1)) * 8, GP);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best[i], 1);
+          const int oa = __shfl_xor_sync(0xffffffffu, arg[i], 1);
+          const bool mine = best[i] > ob || (best[i] == ob && arg[i] < oa);
+          if (!mine) arg[i] = -1;   // the partner lane owns the maximum of this channel
+        }
+        if (!live) continue;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const int dz = pd * 2 + (j >> 1), hy = ph * 2 + (j & 1);
+          const long long v = ((long long)dz * H + hy) * W + wx;
+          const int J = (j >> 1) * 4 + (j & 1) * 2 + (wx & 1);
+          float ny[8], nx[8], G[8];
+          norms(v, dz, hy, wx, ny, nx);
+          ld_grad8(gp_ + (size_t)v * 8, G);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) G[i] += (arg[i] == J) ? GP[i] : 0.f;
+          accumulate(v, ny, nx, G);
+        }
+      }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float tot = warp_xreduce32(red, lane);
@@ -373,8 +395,8 @@ __global__ void __launch_bounds__(256) cat_bwd_a_kernel(const __grid_constant__ 
 int launch_cat_bwd_a(const CatBwdArgs& a, cudaStream_t st) {
   const long long V = dims_vox(a.d);
   const bool pool = a.gp != nullptr, hasx = a.x != nullptr;
-  const long long items = pool ? V / 8 : V;
-  dim3 grid((unsigned)std::min<long long>((items + 255) / 256, 148 * 4), a.C / 8, a.d.N);
+  const int planes = pool ? a.d.D / 2 : a.d.D;
+  dim3 grid((unsigned)std::min(planes, 148 * 2), a.C / 8, a.d.N);
   if (hasx && pool) cat_bwd_a_kernel<true, true><<<grid, 256, 0, st>>>(a);
   else if (hasx) cat_bwd_a_kernel<true, false><<<grid, 256, 0, st>>>(a);
   else if (pool) cat_bwd_a_kernel<false, true><<<grid, 256, 0, st>>>(a);
@@ -402,8 +424,11 @@ __global__ void __launch_bounds__(256) cat_bwd_x_kernel(const __grid_constant__ 
   for (int i = 0; i < 32; ++i) red[i] = 0.f;
   const act_t* rawp = a.raw + ((size_t)n * a.raw_chunks + k) * V * 8;
   const grad_t* dnp = a.dn + ((size_t)n * a.dn_chunks + k) * V * 8;
-  for (long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x; v < V; v += (long long)gridDim.x * blockDim.x) {
-    const int wx = (int)(v % a.d.W), hy = (int)((v / a.d.W) % a.d.H), dz = (int)(v / ((long long)a.d.W * a.d.H));
+  const int W = a.d.W, H = a.d.H;
+  for (int dz = blockIdx.x; dz < a.d.D; dz += gridDim.x)
+  for (int t = threadIdx.x; t < H * W; t += blockDim.x) {
+    const int hy = t / W, wx = t - hy * W;
+    const long long v = ((long long)dz * H + hy) * W + wx;
     float f[8], dn[8];
     chunk_to_floats(ld_chunk_stream(rawp + (size_t)v * 8), f);
     ld_grad8(dnp + (size_t)v * 8, dn);
@@ -434,8 +459,7 @@ __global__ void __launch_bounds__(256) cat_bwd_x_kernel(const __grid_constant__ 
 }
 
 int launch_cat_bwd_x(const CatBwdXArgs& a, cudaStream_t st) {
-  const long long V = dims_vox(a.d);
-  dim3 grid((unsigned)std::min<long long>((V + 255) / 256, 148 * 4), a.C / 8, a.d.N);
+  dim3 grid((unsigned)std::min(a.d.D, 148 * 2), a.C / 8, a.d.N);
   cat_bwd_x_kernel<<<grid, 256, 0, st>>>(a);
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
