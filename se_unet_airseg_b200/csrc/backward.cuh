@@ -74,6 +74,10 @@ int launch_cat_bwd_x(const CatBwdXArgs& a, cudaStream_t st);
 // adjoint of launch_upsample2: gsrc (C ch at sd) = Up2^T(gdst slice)
 int launch_upsample2_bwd(const grad_t* gdst, int gdst_chunks, int gdst_off, int C, Dims sd, grad_t* gsrc, cudaStream_t st);
 
+// separable version on fp32 gradient planes (three 1-D passes); tmp1 >= N*C*(2D*2H*W) floats, tmp2 >= N*C*(2D*H*W) floats
+int launch_upsample2_bwd_sep(const grad_t* gdst, int gdst_chunks, int gdst_off, int C, Dims sd, grad_t* gsrc, float* tmp1, float* tmp2,
+                             cudaStream_t st);
+
 // adjoint of the head: dT_l = Up_{2^l}^T(dpred) for one level, and sum(dpred) for the bias
 int launch_head_bwd_level(const float* dpred, Dims full, int level, float* dT, cudaStream_t st);
 // separable version (three 1-D adjoint passes); tmp1 >= N*D*H*(W>>level) floats, tmp2 >= N*D*(H>>level)*(W>>level) floats

@@ -157,7 +157,7 @@ struct seunet_plan {
   size_t dn_off[4], dy_off[4];       // per-level dn (bf16) / dY (storage type) scratch
   size_t dT0_off[4], dT1_off[3];     // head-accumulator gradients (level 0 aliases dpred)
   size_t bwd_red_off, bwd_red_bytes; // zeroed at the start of every backward
-  size_t redS_off, redSx_off, dwse_off, dwse2_off, dweff_off, dcst_off, dymax_off, scale_off, partial_off, htmp1_off, htmp2_off;
+  size_t redS_off, redSx_off, dwse_off, dwse2_off, dweff_off, dcst_off, dymax_off, scale_off, partial_off, htmp1_off, htmp2_off, utmp1_off, utmp2_off;
   uint8_t* ws = nullptr;
   uint8_t* wimg = nullptr;
   XOffsets xo;                      // per-sample input offsets of the current forward
