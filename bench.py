@@ -271,7 +271,8 @@ def run_ours(args):
     traffic = None
     tp = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))   # one ncu --set full capture at batch 1 (profiles/r01_conv_full_per_layer.txt)
+        traffic = tj.get("dram_bytes_per_launch") * args.batch / max(1, tj.get("batch", 1))
     whole_tf = nwin * FLOP_PER_PATCH / (ms_step * 1e-3) / 1e12
 
     # CPU baseline on this box's host cores: bounded sample of the same workload (2 windows)
@@ -319,7 +320,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=6, help="windows per forward (294 = 6 * 49)")
+    ap.add_argument("--batch", type=int, default=7, help="windows per forward (294 = 7 * 42; 7 fills the 148 persistent conv CTAs slightly better than 6)")
     ap.add_argument("--streams", type=int, default=2, help="CUDA streams alternating over window batches (overlaps HBM-bound and tensor-bound kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
