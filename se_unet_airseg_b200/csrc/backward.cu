@@ -532,43 +532,6 @@ int launch_upsample2_bwd(const grad_t* gdst, int gdst_chunks, int gdst_off, int 
   return 0;
 }
 
-// head adjoint for one level: one warp per low-resolution voxel gathers over the (d,h,w) output window
-__global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__ dpred, Dims full, int level, float* __restrict__ dT) {
-  const int n = blockIdx.y;
-  const int Ds = full.D >> level, Hs = full.H >> level, Ws = full.W >> level;
-  const long long Vs = (long long)Ds * Hs * Ws, V = dims_vox(full);
-  const int lane = threadIdx.x & 31;
-  const long long j = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (j >= Vs) return;
-  const int jw = (int)(j % Ws), jh = (int)((j / Ws) % Hs), jd = (int)(j / ((long long)Ws * Hs));
-  int dlo, dhi, hlo, hhi, wlo, whi;
-  axis_range(jd, Ds, full.D, dlo, dhi);
-  axis_range(jh, Hs, full.H, hlo, hhi);
-  axis_range(jw, Ws, full.W, wlo, whi);
-  const float* gp = dpred + (size_t)n * V;
-  const int nh = hhi - hlo + 1, nw = whi - wlo + 1;
-  float acc = 0.f;
-  for (int od = dlo; od <= dhi; ++od) {
-    const float wd = axis_weight(od, jd, Ds, full.D);
-    if (wd == 0.f) continue;
-    for (int t = lane; t < nh * nw; t += 32) {
-      const int oh = hlo + t / nw, ow = wlo + t % nw;
-      const float w = wd * axis_weight(oh, jh, Hs, full.H) * axis_weight(ow, jw, Ws, full.W);
-      if (w != 0.f) acc = fmaf(w, __ldg(gp + ((size_t)od * full.H + oh) * full.W + ow), acc);
-    }
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) dT[(size_t)n * Vs + j] = acc;
-}
-
-int launch_head_bwd_level(const float* dpred, Dims full, int level, float* dT, cudaStream_t st) {
-  const long long Vs = (long long)(full.D >> level) * (full.H >> level) * (full.W >> level);
-  dim3 grid((unsigned)((Vs + 7) / 8), full.N);
-  head_bwd_kernel<<<grid, 256, 0, st>>>(dpred, full, level, dT);
-  SEUNET_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
 __global__ void __launch_bounds__(256) sum_kernel(const float* __restrict__ src, long long n, float* __restrict__ dst) {
   double s = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s += src[i];

@@ -79,8 +79,7 @@ int launch_upsample2_bwd_sep(const grad_t* gdst, int gdst_chunks, int gdst_off, 
                              cudaStream_t st);
 
 // adjoint of the head: dT_l = Up_{2^l}^T(dpred) for one level, and sum(dpred) for the bias
-int launch_head_bwd_level(const float* dpred, Dims full, int level, float* dT, cudaStream_t st);
-// separable version (three 1-D adjoint passes); tmp1 >= N*D*H*(W>>level) floats, tmp2 >= N*D*(H>>level)*(W>>level) floats
+// three 1-D adjoint passes; tmp1 >= N*D*H*(W>>level) floats, tmp2 >= N*D*(H>>level)*(W>>level) floats
 int launch_head_bwd_level_sep(const float* dpred, Dims full, int level, float* dT, float* tmp1, float* tmp2, cudaStream_t st);
 int launch_sum(const float* src, long long n, float* dst /* single float, overwritten */, cudaStream_t st);
 

@@ -317,52 +317,6 @@ int launch_apply_cat(int C, const CatArgs& a, cudaStream_t st) {
 }
 
 // =============================================================================================
-// trilinear interpolation helpers, align_corners=True (ATen area_pixel_compute_source_index)
-// =============================================================================================
-struct Lerp { int i0, i1; float l0, l1; };
-__device__ __forceinline__ Lerp lerp_ac(int dst, int in_size, int out_size) {
-  const float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
-  const float src = scale * (float)dst;
-  Lerp r;
-  r.i0 = (int)src;
-  r.i1 = r.i0 + (r.i0 < in_size - 1 ? 1 : 0);
-  r.l1 = src - (float)r.i0;
-  r.l0 = 1.f - r.l1;
-  return r;
-}
-
-__global__ void __launch_bounds__(256) upsample2_kernel(const act_t* __restrict__ src, Dims sd, act_t* __restrict__ dst,
-                                                        int dst_chunks, int dst_off, int src_chunks) {
-  const int n = blockIdx.z, k = blockIdx.y;
-  const int Do = sd.D * 2, Ho = sd.H * 2, Wo = sd.W * 2;
-  const long long Vo = (long long)Do * Ho * Wo, Vs = dims_vox(sd);
-  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (v >= Vo) return;
-  const int wx = (int)(v % Wo), hy = (int)((v / Wo) % Ho), dz = (int)(v / ((long long)Wo * Ho));
-  const Lerp ld = lerp_ac(dz, sd.D, Do), lh = lerp_ac(hy, sd.H, Ho), lw = lerp_ac(wx, sd.W, Wo);
-  const act_t* sp = src + ((size_t)n * src_chunks + k) * Vs * 8;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int di = (j & 4) ? ld.i1 : ld.i0, hi = (j & 2) ? lh.i1 : lh.i0, wi = (j & 1) ? lw.i1 : lw.i0;
-    const float wgt = ((j & 4) ? ld.l1 : ld.l0) * ((j & 2) ? lh.l1 : lh.l0) * ((j & 1) ? lw.l1 : lw.l0);
-    float f[8];
-    chunk_to_floats(ld_chunk(sp + (((size_t)di * sd.H + hi) * sd.W + wi) * 8), f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, f[i], acc[i]);
-  }
-  st_chunk(dst + (((size_t)n * dst_chunks + dst_off + k) * Vo + v) * 8, floats_to_chunk(acc));
-}
-
-static int launch_upsample2_v0(const act_t* src, int C, Dims sd, act_t* dst, int dst_chunks, int dst_off, cudaStream_t st) {  // superseded by pointwise2.cu
-  const long long Vo = dims_vox(sd) * 8;
-  dim3 grid((unsigned)((Vo + 255) / 256), C / 8, sd.N);
-  upsample2_kernel<<<grid, 256, 0, st>>>(src, sd, dst, dst_chunks, dst_off, C / 8);
-  SEUNET_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
-// =============================================================================================
 // folded head weights:  weff[blk][n][c] = sum_j hw[2k+j] * drop[n][2k+j] * W2[j][c]
 // (conv2 SE_UNet.py:33/80, DropLayer 89-97, dc0_0/dc0_1 232-233; all linear, so they commute
 //  with the trilinear up-sampling of the side branch)
@@ -390,50 +344,6 @@ int launch_headw(const float* params, const float* drop0, const float* drop1, in
                  float* weff, float* wcst, cudaStream_t st) {
   dim3 grid(a.nblk, N);
   headw_kernel<<<grid, 64, 0, st>>>(params, drop0, drop1, a, weff, wcst);
-  SEUNET_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
-// =============================================================================================
-// head: pred = bias + T(S) + Up2(T(S/2)) + Up4(T(S/4)) [+ Up8(T(S/8))]
-// =============================================================================================
-__device__ __forceinline__ float sample_ac(const float* __restrict__ T, int Ds, int Hs, int Ws, int dz, int hy, int wx,
-                                           int Do, int Ho, int Wo) {
-  const Lerp ld = lerp_ac(dz, Ds, Do), lh = lerp_ac(hy, Hs, Ho), lw = lerp_ac(wx, Ws, Wo);
-  float acc = 0.f;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int di = (j & 4) ? ld.i1 : ld.i0, hi = (j & 2) ? lh.i1 : lh.i0, wi = (j & 1) ? lw.i1 : lw.i0;
-    const float wgt = ((j & 4) ? ld.l1 : ld.l0) * ((j & 2) ? lh.l1 : lh.l0) * ((j & 1) ? lw.l1 : lw.l0);
-    acc = fmaf(wgt, __ldg(T + ((size_t)di * Hs + hi) * Ws + wi), acc);
-  }
-  return acc;
-}
-
-__global__ void __launch_bounds__(256) head_kernel(const __grid_constant__ HeadArgs a) {
-  const int n = blockIdx.y;
-  const Dims d = a.d;
-  const long long V = dims_vox(d);
-  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (v >= V) return;
-  const int wx = (int)(v % d.W), hy = (int)((v / d.W) % d.H), dz = (int)(v / ((long long)d.W * d.H));
-  float p0 = a.bias0[0] + a.T0[0][(size_t)n * V + v];
-  float p1 = a.bias1[0] + a.T1[0][(size_t)n * V + v];
-#pragma unroll
-  for (int l = 1; l < 4; ++l) {
-    const int Ds = d.D >> l, Hs = d.H >> l, Ws = d.W >> l;
-    const size_t Vs = (size_t)Ds * Hs * Ws;
-    p0 += sample_ac(a.T0[l] + n * Vs, Ds, Hs, Ws, dz, hy, wx, d.D, d.H, d.W);
-    if (l < 3) p1 += sample_ac(a.T1[l] + n * Vs, Ds, Hs, Ws, dz, hy, wx, d.D, d.H, d.W);
-  }
-  a.pred0[(size_t)n * V + v] = p0;
-  a.pred1[(size_t)n * V + v] = p1;
-}
-
-static int launch_head_v0(const HeadArgs& a, cudaStream_t st) {  // superseded by pointwise2.cu
-  const long long V = dims_vox(a.d);
-  dim3 grid((unsigned)((V + 255) / 256), a.d.N);
-  head_kernel<<<grid, 256, 0, st>>>(a);
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
