@@ -14,7 +14,7 @@ __device__ __forceinline__ void atomic_max_pos(unsigned int* p, float v) { atomi
 // SSE block backward, pass A
 // =============================================================================================
 template <int C, int GATES>
-__global__ void __launch_bounds__(256) sse_bwd_a_kernel(const __grid_constant__ SseBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant__ SseBwdArgs a) {
   constexpr int LPV = C / 8;     // lanes cooperating on one voxel (one 8-channel chunk each)
   constexpr int VPW = 32 / LPV;  // voxels per warp
   __shared__ float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
@@ -43,10 +43,34 @@ __global__ void __launch_bounds__(256) sse_bwd_a_kernel(const __grid_constant__ 
     for (int o = 1; o < LPV; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   };
-  for (long long vb = ((long long)blockIdx.x * 8 + warp) * VPW; vb < a.V; vb += (long long)gridDim.x * 8 * VPW) {
+  // Software pipeline: the loads of the NEXT voxel group are issued before the arithmetic of the current one.  The kernel
+  // runs at 25 % occupancy (106 registers), so the bytes in flight per warp decide the achieved bandwidth (ncu: stalled
+  // on long-scoreboard, 2.9 TB/s without the prefetch).
+  const long long vstep = (long long)gridDim.x * 8 * VPW;
+  const act_t* rawp = a.raw + ((size_t)n * a.raw_chunks + k) * a.V * 8;
+  const grad_t* de0p = a.dE0 ? a.dE0 + ((size_t)n * a.dE0_chunks + a.dE0_off + k) * a.V * 8 : nullptr;
+  const float* dTp = a.dT + (size_t)n * a.V;
+  Chunk8 raw_n;
+  float de0_n[8], dT_n = 0.f;
+  auto prefetch = [&](long long v) {
+    raw_n = ld_chunk_stream(rawp + (size_t)v * 8);
+    dT_n = dTp[v];
+    if (de0p) ld_grad8(de0p + (size_t)v * 8, de0_n);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) de0_n[i] = 0.f;
+    }
+  };
+  const long long vb0 = ((long long)blockIdx.x * 8 + warp) * VPW;
+  if (vb0 < a.V) prefetch(vb0 + vsub);
+  for (long long vb = vb0; vb < a.V; vb += vstep) {
     const long long v = vb + vsub;   // V is a multiple of 32, so the whole warp is in range
-    float f[8], nn[8], av[8], e0[8];
-    chunk_to_floats(ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8), f);
+    float f[8], nn[8], av[8], e0[8], de0[8];
+    chunk_to_floats(raw_n, f);
+    const float dT = dT_n;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) de0[i] = de0_n[i];
+    if (vb + vstep < a.V) prefetch(v + vstep);
     float p1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -67,13 +91,6 @@ __global__ void __launch_bounds__(256) sse_bwd_a_kernel(const __grid_constant__ 
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) e0[i] = a1[i] * g2;
-    const float dT = a.dT[(size_t)n * a.V + v];
-    float de0[8];
-    if (a.dE0) ld_grad8(a.dE0 + (((size_t)n * a.dE0_chunks + a.dE0_off + k) * a.V + v) * 8, de0);
-    else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) de0[i] = 0.f;
-    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) de0[i] = fmaf(s_weff[k * 8 + i], dT, de0[i]);
     float da1[8], k2 = 0.f;
