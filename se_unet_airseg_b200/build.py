@@ -37,6 +37,8 @@ def build(force=False, bf16=None, verbose=False):
     if bf16 is None:
         bf16 = os.environ.get("SEUNET_ACT_BF16", "0") == "1"
     extra = ["-DSEUNET_ACT_BF16"] if bf16 else []
+    if os.environ.get("SEUNET_GRAD_BF16", "0") == "1":   # experiment only: bf16 gradient planes miss the 1e-2 gradient tolerance
+        extra.append("-DSEUNET_GRAD_BF16")
     want = _source_hash(extra)
     if not force and os.path.exists(LIB) and os.path.exists(STAMP):
         with open(STAMP) as fh:

@@ -78,6 +78,23 @@ __device__ __forceinline__ Chunk8 floats_to_chunk_bf16(const float* f) {
   }
   return c;
 }
+__device__ __forceinline__ Chunk8 ld_chunk(const void* p) {
+  Chunk8 c;
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  c.u[0] = v.x; c.u[1] = v.y; c.u[2] = v.z; c.u[3] = v.w;
+  return c;
+}
+// streaming variants: data touched once per kernel should not pollute L1
+__device__ __forceinline__ Chunk8 ld_chunk_stream(const void* p) {
+  Chunk8 c;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(c.u[0]), "=r"(c.u[1]), "=r"(c.u[2]), "=r"(c.u[3]) : "l"(p));
+  return c;
+}
+__device__ __forceinline__ void st_chunk(void* p, const Chunk8& c) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(c.u[0], c.u[1], c.u[2], c.u[3]);
+}
+
 // Gradients w.r.t. activations (dn scratch and the per-buffer gradient accumulators) are fp32 by default: the weight
 // gradient is a heavily cancelling sum, and bf16 storage of its inputs costs ~10x the 1e-2 tolerance at small volumes.
 // -DSEUNET_GRAD_BF16 halves that traffic at the price of accuracy.
@@ -107,23 +124,6 @@ __device__ __forceinline__ void st_grad8(grad_t* p, const float* f) {
   reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
 }
 #endif
-
-__device__ __forceinline__ Chunk8 ld_chunk(const void* p) {
-  Chunk8 c;
-  const uint4 v = *reinterpret_cast<const uint4*>(p);
-  c.u[0] = v.x; c.u[1] = v.y; c.u[2] = v.z; c.u[3] = v.w;
-  return c;
-}
-// streaming variants: data touched once per kernel should not pollute L1
-__device__ __forceinline__ Chunk8 ld_chunk_stream(const void* p) {
-  Chunk8 c;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-               : "=r"(c.u[0]), "=r"(c.u[1]), "=r"(c.u[2]), "=r"(c.u[3]) : "l"(p));
-  return c;
-}
-__device__ __forceinline__ void st_chunk(void* p, const Chunk8& c) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(c.u[0], c.u[1], c.u[2], c.u[3]);
-}
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
 __device__ __forceinline__ float lrelu_(float x) { return x > 0.f ? x : 0.01f * x; }
