@@ -104,8 +104,10 @@ int launch_input_prep(const float* x, const long long* xs, const XOffsets& xo, i
 // SSE block apply:  y -> IN -> LeakyReLU -> sSE gate(s) -> e0 (+ folded conv2/head contribution)
 // (SE_UNet.py:26-33 / 70-80; fold of conv2 + up_sample + dc0_x per SURVEY App. C)
 // =============================================================================================
+// (register caps chosen by A/B: C = 64 gains 17 % from three blocks per SM instead of two; the narrower variants need <= 64
+// registers for four blocks (C = 32) / 42 for six (C <= 16) - with fewer resident blocks they are 7-10 % slower)
 template <int C, int GATES>
-__global__ void __launch_bounds__(256) apply_sse_kernel(const __grid_constant__ SseArgs a) {
+__global__ void __launch_bounds__(256, C == 64 ? 3 : (C == 32 ? 4 : 6)) apply_sse_kernel(const __grid_constant__ SseArgs a) {
   __shared__ __align__(16) float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -201,7 +203,7 @@ int launch_apply_sse(int C, int N, const SseArgs& a, cudaStream_t st) {
 // over all channel chunks: index arithmetic, the x-branch loads and the per-channel constants are amortised over C
 // channels, every load/store is a coalesced 16 B per lane, and the w pair of the pooling window is reduced with a shuffle.
 template <int C, bool HASX, bool POOL>
-__global__ void __launch_bounds__(256) apply_cat_kernel(const __grid_constant__ CatArgs a) {
+__global__ void __launch_bounds__(256, 3) apply_cat_kernel(const __grid_constant__ CatArgs a) {
   __shared__ __align__(16) float s_mean[C], s_rstd[C], s_ax[C], s_bx[C], s_cx[C];
   const int n = blockIdx.z;
   const int W = a.d.W, H = a.d.H;
