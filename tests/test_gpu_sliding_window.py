@@ -48,3 +48,40 @@ def test_sliding_window_matches_oracle(batch):
     assert (mask.cpu().numpy().astype(bool) == mask_ref)[conf].all()
     host_mask = sw.predict(img.numpy())
     assert host_mask.dtype == torch.uint8 and torch.equal(host_mask, mask.cpu())
+
+
+def test_full_size_volume_properties():
+    """BASELINE config-2 size (512x512x400, 294 windows of 128^3).  The CPU oracle would need ~7 minutes, so the whole-volume
+    path is checked through size-independent properties: (a) the corner block that only ONE window covers equals that
+    window's own sigmoid output; (b) a block covered by 8 windows equals the mean of those 8 window outputs; (c) the result does
+    not depend on the window batch / stream configuration beyond fp32 summation order; (d) mask == (mean probability >= 0.5)."""
+    from se_unet_airseg_b200 import SE_UNet
+    from se_unet_airseg_b200.inference import SlidingWindowPredictor
+    sd = oracle.init_params(2, 1, seed=777)
+    m = SE_UNet(2, 1)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    img = _synthetic_ct((512, 512, 400), 5).cuda()
+    sw = SlidingWindowPredictor(m)                      # defaults: cube 128, step 64, batch 7, 2 streams
+    mask, prob = sw.predict_device(img, return_prob=True)
+    prob = prob.clone(); mask = mask.clone()
+    assert tuple(prob.shape) == (512, 512, 400) and bool(torch.isfinite(prob).all())
+    assert torch.equal(mask.bool(), prob >= 0.5)
+    # windows evaluated directly through the module on the same normalised input
+    x2 = oracle.two_channel(img.cpu().to(torch.float64) - 1024.0).to(torch.float32).cuda()
+
+    def window(x0, y0, z0):
+        with torch.no_grad():
+            return torch.sigmoid(m(x2[None, :, x0:x0 + 128, y0:y0 + 128, z0:z0 + 128])[1])[0, 0]
+
+    w000 = window(0, 0, 0)
+    assert (prob[:64, :64, :64] - w000[:64, :64, :64]).abs().max().item() <= 1e-5
+    acc = torch.zeros(64, 64, 64, device="cuda")
+    for x0 in (0, 64):
+        for y0 in (0, 64):
+            for z0 in (0, 64):
+                acc += window(x0, y0, z0)[64 - x0:128 - x0, 64 - y0:128 - y0, 64 - z0:128 - z0]
+    assert (prob[64:128, 64:128, 64:128] - acc / 8).abs().max().item() <= 1e-5
+    sw2 = SlidingWindowPredictor(m, batch=3, streams=1)
+    _, prob2 = sw2.predict_device(img, return_prob=True)
+    assert (prob2 - prob).abs().max().item() <= 1e-5
