@@ -160,3 +160,27 @@ def test_backward_guard_against_workspace_reuse():
     with pytest.raises(SeunetError):
         p0.sum().backward()
     q0.sum().backward()
+
+
+def test_backward_full_size_is_linear_in_the_output_gradient():
+    """BASELINE training patch size (128^3).  CPU autograd of the oracle takes ~25 s per patch, so the full-size backward is
+    checked through a size-independent property: with the forward state fixed, the backward is a LINEAR map of the output
+    gradients, grads(a + b) = grads(a) + grads(b) (tensor-core dgrad/wgrad chains, the per-layer power-of-two dY scaling,
+    InstanceNorm/gate/pool adjoints and the head fold all have to commute with addition), and it is not identically zero."""
+    m, _ = _model(2, 4242, train=False)
+    g = torch.Generator().manual_seed(77)
+    x = torch.rand(1, 2, 128, 128, 128, generator=g).cuda()
+    ga0, ga1 = (torch.randn(1, 1, 128, 128, 128, generator=g).cuda() * 1e-3 for _ in range(2))
+    gb0, gb1 = (torch.randn(1, 1, 128, 128, 128, generator=g).cuda() * 1e-3 for _ in range(2))
+    params = [p for n, p in m.named_parameters() if not n.startswith("dc62") and not n.endswith("conv1.bias")]
+
+    def grads(d0, d1):
+        p0, p1 = m(x)
+        gs = torch.autograd.grad([p0, p1], params, [d0, d1], allow_unused=True)
+        return torch.cat([gg.reshape(-1) for gg in gs if gg is not None]).double()
+
+    a, b, ab = grads(ga0, ga1), grads(gb0, gb1), grads(ga0 + gb0, ga1 + gb1)
+    assert a.norm().item() > 0 and b.norm().item() > 0
+    rel = ((a + b) - ab).norm().item() / ab.norm().item()
+    print(f"128^3 backward linearity: |g(a)+g(b)-g(a+b)| / |g(a+b)| = {rel:.3e}")
+    assert rel <= REL_TOL
