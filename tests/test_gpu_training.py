@@ -118,3 +118,53 @@ def test_trainer_step_equals_autograd_plus_torch_adamw(stage):
     assert diffs.mean().item() <= 5e-6
     assert (diffs > 2e-5).float().mean().item() <= 0.05
     assert torch.equal(mb.dc62.conv1.weight.cpu(), sd["dc62.conv1.weight"])
+
+
+def test_reference_training_loop_runs_unchanged_on_the_drop_in_module():
+    """The reference's own training idiom (train.py:186-188, 323, 597-603): nn.DataParallel wrapper, torch.optim.AdamW on
+    model.parameters(), torch loss on the two outputs, loss.backward(), optimizer.step(), model.module.state_dict().
+    With one visible GPU DataParallel.forward short-circuits to the module."""
+    from se_unet_airseg_b200 import SE_UNet
+    torch.manual_seed(5)
+    model = SE_UNet(in_channel=2, n_classes=1).cuda()
+    model = torch.nn.DataParallel(model, device_ids=[0])
+    optimizer = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    model.train()
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(2, 2, 32, 32, 32, generator=g).cuda()
+    label = torch.zeros(2, 1, 32, 32, 32)
+    label[:, :, 8:24, 14:18, 14:18] = 1.0
+    label = label.cuda()
+    x[:, :, 8:24, 14:18, 14:18] *= 0.2          # the "airway" is darker
+
+    def dice_loss(pred, target):                 # train.py:51-57
+        smooth = 1.0
+        iflat, tflat = pred.view(-1), target.view(-1)
+        inter = (iflat * tflat).sum()
+        return 1 - (2.0 * inter + smooth) / (iflat.sum() + tflat.sum() + smooth)
+
+    before = {k: v.detach().clone() for k, v in model.module.state_dict().items()}
+    losses = []
+    for _ in range(12):
+        p_en, p_de = model(x)
+        loss = dice_loss(torch.sigmoid(p_de), label) + dice_loss(torch.sigmoid(p_en), label)   # train.py:597-599
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        losses.append(loss.item())
+    print("reference-style loop losses:", [round(v, 4) for v in losses])
+    assert losses[-1] < losses[0] - 0.02, "loss did not decrease"
+    after = model.module.state_dict()
+    assert len(after) == 117 and list(after.keys()) == list(before.keys())
+    changed = [k for k in after if not torch.equal(after[k], before[k])]
+    frozen = [k for k in after if k not in changed]
+    assert all(k.startswith("dc62") for k in frozen), f"parameters without updates: {frozen[:5]}"   # dc62 is dead code in the graph
+    # the saved checkpoint loads back into a fresh module exactly like train.py/prediction.py do
+    fresh = SE_UNet(in_channel=2, n_classes=1)
+    fresh.load_state_dict({k: v.cpu() for k, v in after.items()}, strict=False)
+    fresh = fresh.cuda().eval()
+    model.eval()
+    with torch.no_grad():
+        a0, a1 = model(x)
+        b0, b1 = fresh(x)
+    assert torch.equal(a1, b1) and torch.equal(a0, b0)
