@@ -123,6 +123,12 @@ __device__ __forceinline__ void st_grad8(grad_t* p, const float* f) {
   reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
   reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
 }
+// p[0..7] += f[0..7] as two fire-and-forget vector reductions executed in L2: no read round trip through the SM
+#define SEUNET_HAVE_RED_GRAD8 1
+__device__ __forceinline__ void red_grad8(grad_t* p, const float* f) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p + 4), "f"(f[4]), "f"(f[5]), "f"(f[6]), "f"(f[7]) : "memory");
+}
 #endif
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }

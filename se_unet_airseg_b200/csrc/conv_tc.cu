@@ -356,6 +356,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               const size_t ek = eo + (size_t)k * a.D * plane_elems;
               if (a.out_bf16) {   // gradient-format output (grad_t), optionally accumulating
                 grad_t* ok = reinterpret_cast<grad_t*>(a.out) + ek;
+#ifdef SEUNET_HAVE_RED_GRAD8
+                // gradient accumulation of fan-out nodes: vector reduction in L2 instead of load + add + store (the read
+                // latency, once per plane and chunk, made the epilogue the bottleneck of the accumulating dgrads)
+                if (a.accum_out) red_grad8(ok, f + 8 * k);
+                else st_grad8(ok, f + 8 * k);
+#else
                 if (a.accum_out) {
                   float old[8];
                   ld_grad8_cached(ok, old);
@@ -363,6 +369,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
                   for (int i = 0; i < 8; ++i) f[8 * k + i] += old[i];
                 }
                 st_grad8(ok, f + 8 * k);
+#endif
               } else {
                 st_chunk(reinterpret_cast<uint16_t*>(a.out) + ek, floats_to_chunk(f + 8 * k));
               }
