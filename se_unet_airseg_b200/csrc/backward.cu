@@ -166,7 +166,12 @@ template <int C>
 static int launch_sse_bwd_a_c(const SseBwdArgs& a, cudaStream_t st) {
   constexpr int VPB = 8 * (32 / (C / 8));
   const long long need = (a.V + VPB - 1) / VPB;
-  dim3 grid((unsigned)std::min<long long>(need, 148 * 8), a.N);
+  // Every block ends with 5*C same-address atomics per sample: at the coarse levels (few voxels) thousands of one-iteration
+  // blocks spent their time in that tail and in the per-block statistics prologue.  Give each warp >= 16 voxel groups, but
+  // keep >= 4 blocks per SM in flight over the whole batch.
+  const long long floor_blocks = (148 * 4 + a.N - 1) / a.N;
+  const long long gx = std::min<long long>(need, std::max<long long>(floor_blocks, std::min<long long>(148 * 8, need / 16)));
+  dim3 grid((unsigned)gx, a.N);
   if (a.wse2) sse_bwd_a_kernel<C, 2><<<grid, 256, 0, st>>>(a);
   else sse_bwd_a_kernel<C, 1><<<grid, 256, 0, st>>>(a);
   SEUNET_CUDA_CHECK(cudaGetLastError());
