@@ -321,7 +321,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=7, help="windows per forward (294 = 7 * 42; 7 fills the 148 persistent conv CTAs slightly better than 6)")
-    ap.add_argument("--streams", type=int, default=2, help="CUDA streams alternating over window batches (overlaps HBM-bound and tensor-bound kernels)")
+    ap.add_argument("--streams", type=int, default=3, help="CUDA streams alternating over window batches (overlaps HBM-bound and tensor-bound kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     args = ap.parse_args()

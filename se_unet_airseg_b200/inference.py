@@ -45,7 +45,7 @@ def coverage_counts(length, starts, cube):
 class SlidingWindowPredictor:
     """Runs `model` (se_unet_airseg_b200.SE_UNet on a CUDA device, eval mode like prediction.py:64) over a CT volume."""
 
-    def __init__(self, model, cube=128, step=64, batch=7, threshold=0.5, streams=2):
+    def __init__(self, model, cube=128, step=64, batch=7, threshold=0.5, streams=3):
         """streams > 1: consecutive window batches run on different CUDA streams with their own plan workspaces, so the
         HBM-bound passes of one batch overlap the tensor-bound convolutions of the other (both fit on an SM together)."""
         self.model = model
