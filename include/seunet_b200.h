@@ -148,6 +148,10 @@ int seunet_adamw_step(float* params, const float* grads, float* exp_avg, float* 
 /* two_channel(img + offset): img int16 (dtype 0) or fp32 (dtype 1) of nvox voxels -> out[2][nvox] fp32,
  * HU windows [-1024,1024] and [-1000,500] scaled to [0,1]; evaluated in fp64 like the numpy reference. */
 int seunet_hu_windows(const void* img, int dtype, int64_t nvox, double offset, float* out, seunet_stream_t stream);
+/* Same on a slab of nvox voxels of a larger volume: channel 1 is written channel_stride floats after channel 0 (lets the
+ * host copy of a volume be pipelined slab by slab with the windows that only need its first planes). */
+int seunet_hu_windows_slab(const void* img, int dtype, int64_t nvox, int64_t channel_stride, double offset, float* out,
+                           seunet_stream_t stream);
 /* acc[window b] += sigmoid(logits[b]) for B windows of size (cd,ch,cw) starting at HOST starts[b][3]
  * inside the (X,Y,Z) fp32 accumulator volume (prediction.py:103-106). */
 int seunet_window_accumulate(const float* logits, const int* starts, int B, int cd, int ch, int cw, float* acc, int X,

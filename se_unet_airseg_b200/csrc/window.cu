@@ -7,26 +7,33 @@
 // prediction.py:69 (img - 1024) and two_channel() (prediction.py:39-49), evaluated in float64 exactly
 // like the numpy reference and rounded once to fp32 (x = torch.from_numpy(img.astype(np.float32))).
 template <typename T>
-__global__ void __launch_bounds__(256) hu_windows_kernel(const T* __restrict__ img, long long n, double offset,
+__global__ void __launch_bounds__(256) hu_windows_kernel(const T* __restrict__ img, long long n, long long cstride, double offset,
                                                          float* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double v = (double)img[i] + offset;
     const double a = fmin(fmax(v, -1024.0), 1024.0);
     const double b = fmin(fmax(v, -1000.0), 500.0);
     out[i] = (float)((a + 1024.0) / 2048.0);
-    out[n + i] = (float)((b + 1000.0) / 1500.0);
+    out[cstride + i] = (float)((b + 1000.0) / 1500.0);
   }
+}
+
+extern "C" int seunet_hu_windows_slab(const void* img, int dtype, int64_t nvox, int64_t channel_stride, double offset, float* out,
+                                      seunet_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nvox <= 0) return 0;
+  if (channel_stride < nvox) { seunet_set_error("hu_windows: channel stride smaller than the slab"); return 1; }
+  const int blocks = (int)((nvox + 255) / 256 < 148 * 16 ? (nvox + 255) / 256 : 148 * 16);
+  if (dtype == 0) hu_windows_kernel<short><<<blocks, 256, 0, st>>>((const short*)img, nvox, channel_stride, offset, out);
+  else if (dtype == 1) hu_windows_kernel<float><<<blocks, 256, 0, st>>>((const float*)img, nvox, channel_stride, offset, out);
+  else { seunet_set_error("hu_windows: dtype %d unsupported (0=int16, 1=float32)", dtype); return 1; }
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int seunet_hu_windows(const void* img, int dtype, int64_t nvox, double offset, float* out,
                                  seunet_stream_t stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  const int blocks = (int)((nvox + 255) / 256 < 148 * 16 ? (nvox + 255) / 256 : 148 * 16);
-  if (dtype == 0) hu_windows_kernel<short><<<blocks, 256, 0, st>>>((const short*)img, nvox, offset, out);
-  else if (dtype == 1) hu_windows_kernel<float><<<blocks, 256, 0, st>>>((const float*)img, nvox, offset, out);
-  else { seunet_set_error("hu_windows: dtype %d unsupported (0=int16, 1=float32)", dtype); return 1; }
-  SEUNET_CUDA_CHECK(cudaGetLastError());
-  return 0;
+  return seunet_hu_windows_slab(img, dtype, nvox, nvox, offset, out, stream);
 }
 
 struct WinStarts { int n; int s[32][3]; };

@@ -70,9 +70,11 @@ class SlidingWindowPredictor:
         return g
 
     @torch.no_grad()
-    def predict_device(self, img_dev, hu_offset=-1024.0, return_prob=False):
+    def predict_device(self, img_dev, hu_offset=-1024.0, return_prob=False, _slab_events=None):
         """img_dev: (X, Y, Z) int16 or fp32 CUDA tensor holding the stored CT values (HU + 1024, prediction.py:68-69).
-        Returns the uint8 mask (X, Y, Z) on the device (and the mean probability if return_prob)."""
+        Returns the uint8 mask (X, Y, Z) on the device (and the mean probability if return_prob).
+        _slab_events (internal, used by predict()): [(x_end, event)] - the two-HU-window input has already been produced slab
+        by slab on a copy stream; a window batch waits only for the slabs it reads."""
         L = _lib.lib()
         m = self.model
         if m.in_channel != 2:
@@ -84,9 +86,10 @@ class SlidingWindowPredictor:
         g = self._geometry((X, Y, Z), dev)
         st = _lib.stream_ptr()
         dtype = {torch.int16: 0, torch.float32: 1}[img_dev.dtype]
-        img_dev = img_dev.contiguous()
-        _lib.check(L.seunet_hu_windows(_lib.ptr(img_dev), dtype, X * Y * Z, float(hu_offset), _lib.ptr(g["x2"]), st),
-                   "seunet_hu_windows")
+        if _slab_events is None:
+            img_dev = img_dev.contiguous()
+            _lib.check(L.seunet_hu_windows(_lib.ptr(img_dev), dtype, X * Y * Z, float(hu_offset), _lib.ptr(g["x2"]), st),
+                       "seunet_hu_windows")
         g["acc"].zero_()
         x2 = g["x2"]
         sN, sC, sD, sH, sW = x2.stride()
@@ -108,6 +111,12 @@ class SlidingWindowPredictor:
             b = min(self.batch, len(wins) - i)
             slot = k % len(streams)
             cs = streams[slot]
+            if _slab_events is not None:
+                need = max(w[0] for w in wins[i:i + b]) + cube
+                for x_end, ev in _slab_events:          # every slab below the highest plane this batch reads
+                    cs.wait_event(ev)
+                    if x_end >= need:
+                        break
             with torch.cuda.stream(cs):
                 stp = ctypes.c_void_p(cs.cuda_stream)
                 plan = m._plan(b, cube, cube, cube, 0, dev, slot=slot)
@@ -154,13 +163,45 @@ class SlidingWindowPredictor:
         return buf
 
     @torch.no_grad()
-    def predict(self, img_host, hu_offset=-1024.0):
+    def predict(self, img_host, hu_offset=-1024.0, slab=64):
         """End-to-end call a user makes: host volume (numpy int16/float32 or CPU tensor, ideally pinned) in, host uint8
-        mask out.  One H2D copy of the stored CT values and one D2H copy of the mask."""
+        mask out.  The H2D copy and the HU windowing run slab by slab (along the first axis) on a copy stream, and every window
+        batch waits only for the slabs it reads, so the forward passes start after the first ~128 planes have arrived;
+        one D2H copy of the mask at the end."""
+        L = _lib.lib()
         t = torch.from_numpy(img_host) if isinstance(img_host, np.ndarray) else img_host
         dev = next(p for p in self.model._param_tensors()).device
-        d = t.to(dev, non_blocking=True)
-        mask = self.predict_device(d, hu_offset)
+        if t.dtype not in (torch.int16, torch.float32) or t.dim() != 3:
+            raise ValueError("expected a 3-D int16 or float32 volume")
+        t = t.contiguous()
+        X, Y, Z = t.shape
+        g = self._geometry((X, Y, Z), dev)
+        dtype = {torch.int16: 0, torch.float32: 1}[t.dtype]
+        stage = getattr(self, "_dev_img", None)
+        if stage is None or stage.shape != t.shape or stage.dtype != t.dtype or stage.device != dev:
+            stage = torch.empty(t.shape, dtype=t.dtype, device=dev)
+            self._dev_img = stage
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None or copy_stream.device != dev:
+            copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_stream = copy_stream
+        main = torch.cuda.current_stream(dev)
+        start = torch.cuda.Event()
+        start.record(main)                     # the previous volume's windows must be done with x2 before it is overwritten
+        copy_stream.wait_event(start)
+        events = []
+        plane = Y * Z
+        with torch.cuda.stream(copy_stream):
+            for x0 in range(0, X, slab):
+                x1 = min(X, x0 + slab)
+                stage[x0:x1].copy_(t[x0:x1], non_blocking=True)
+                _lib.check(L.seunet_hu_windows_slab(_lib.ptr(stage[x0:x1]), dtype, (x1 - x0) * plane, X * plane, float(hu_offset),
+                                                    ctypes.c_void_p(g["x2"].data_ptr() + x0 * plane * 4),
+                                                    ctypes.c_void_p(copy_stream.cuda_stream)), "seunet_hu_windows_slab")
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append((x1, ev))
+        mask = self.predict_device(stage, hu_offset, _slab_events=events)
         out = getattr(self, "_host_mask", None)
         if out is None or out.shape != mask.shape:
             out = torch.empty(mask.shape, dtype=torch.uint8, pin_memory=True)
