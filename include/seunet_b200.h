@@ -153,13 +153,16 @@ int seunet_hu_windows(const void* img, int dtype, int64_t nvox, double offset, f
 int seunet_hu_windows_slab(const void* img, int dtype, int64_t nvox, int64_t channel_stride, double offset, float* out,
                            seunet_stream_t stream);
 /* acc[window b] += sigmoid(logits[b]) for B windows of size (cd,ch,cw) starting at HOST starts[b][3]
- * inside the (X,Y,Z) fp32 accumulator volume (prediction.py:103-106). */
-int seunet_window_accumulate(const float* logits, const int* starts, int B, int cd, int ch, int cw, float* acc, int X,
-                             int Y, int Z, int apply_sigmoid, seunet_stream_t stream);
+ * inside the (X,Y,Z) accumulator volume (prediction.py:103-106).  The accumulator is 32-bit FIXED POINT in units of
+ * 2^-acc_log2 (zero it before the first window; pick acc_log2 with max_overlap_count * 2^acc_log2 < 2^31, 26 for the
+ * reference's 128/64 grid): integer sums are order-independent, so window batches on several streams and the partial
+ * volumes of several ranks (one integer SUM all-reduce) give bit-identical results. */
+int seunet_window_accumulate(const float* logits, const int* starts, int B, int cd, int ch, int cw, uint32_t* acc, int X,
+                             int Y, int Z, int apply_sigmoid, int acc_log2, seunet_stream_t stream);
 /* mean = acc / count (prediction.py:109), mask = mean >= threshold. counts_dev: DEVICE int[X+Y+Z] with the
- * per-axis window coverage counts. mask may be NULL; write_mean stores the mean back into acc. */
-int seunet_window_finalize(float* acc, const int* counts_dev, int X, int Y, int Z, float threshold,
-                           unsigned char* mask, int write_mean, seunet_stream_t stream);
+ * per-axis window coverage counts. mask may be NULL; write_mean overwrites acc with the fp32 mean (same 4-byte slots). */
+int seunet_window_finalize(uint32_t* acc, const int* counts_dev, int X, int Y, int Z, float threshold,
+                           unsigned char* mask, int write_mean, int acc_log2, seunet_stream_t stream);
 
 /* ---- post-processing of the mean-probability volume (prediction.py:13-37, 111-116; util.py:58-75) ----
  * scratch: caller-owned DEVICE buffer of seunet_postproc_scratch_bytes(); max_runs bounds the number of row runs (maximal

@@ -120,14 +120,17 @@ class _Plan:
         self.ws = torch.empty(L.seunet_plan_workspace_bytes(h), dtype=torch.uint8, device=device)
         self.wimg = torch.empty(L.seunet_plan_wimg_bytes(h), dtype=torch.uint8, device=device)
         _lib.check(L.seunet_plan_bind(h, _lib.ptr(self.ws), _lib.ptr(self.wimg), _lib.stream_ptr()), "seunet_plan_bind")
-        self.packed_for = None  # (flat data_ptr, version) the weight image was packed from
+        self.nbytes = self.ws.numel() + self.wimg.numel()
+        self.packed_gen = None  # weight generation (see SE_UNet._weights) the tensor-core image was packed from
         self.generation = 0     # bumped by every autograd forward (guards backward against workspace reuse)
 
-    def pack(self, flat):
-        tag = (flat.data_ptr(), flat._version)
-        if self.packed_for != tag:
+    def pack(self, flat, gen):
+        """Re-pack the tensor-core weight image when the parameters changed.  `gen` is the owner's monotonically
+        increasing weight generation - NOT an address/version tag: a re-gathered flat buffer is a fresh tensor whose
+        (data_ptr, _version) can repeat an older one when the caching allocator recycles the block."""
+        if self.packed_gen != gen:
             _lib.check(_lib.lib().seunet_pack_weights(self.handle, _lib.ptr(flat), _lib.stream_ptr()), "seunet_pack_weights")
-            self.packed_for = tag
+            self.packed_gen = gen
 
     def __del__(self):
         try:
@@ -138,7 +141,8 @@ class _Plan:
             pass
 
 
-_MAX_PLANS = 6
+_MAX_PLANS = 12              # bound plans kept per (module replica, device): LRU beyond this count ...
+_MAX_PLAN_BYTES = 96 << 30   # ... or beyond this many bytes of workspaces (a 7-window inference plan holds ~8 GB)
 
 
 class _SEUNetFunction(torch.autograd.Function):
@@ -186,6 +190,18 @@ class _SEUNetFunction(torch.autograd.Function):
         # dc62 is dead code in the reference graph (SE_UNet.py:230): its .grad stays None there too
         grads[ctx.module._dead_param_index] = None
         return (None, None, None, None, None, None, *grads)
+
+
+def _aliases_flat(params, flat):
+    """True when every tensor of `params` is the view of `flat` at its state_dict offset (DataParallelTrainer layout)."""
+    if flat.device != params[0].device:
+        return False
+    base, off = flat.data_ptr(), 0
+    for p in params:
+        if p.dtype != torch.float32 or not p.is_contiguous() or p.data_ptr() != base + 4 * off:
+            return False
+        off += p.numel()
+    return off == flat.numel()
 
 
 class SE_UNet(nn.Module):
@@ -251,6 +267,7 @@ class SE_UNet(nn.Module):
         self._param_paths = [tuple(n.rsplit('.', 1)) for n, _ in self.named_parameters()]
         self._dead_param_index = [i for i, (m, a) in enumerate(self._param_paths) if m == 'dc62.conv1'][0]
         object.__setattr__(self, '_rt', None)
+        object.__setattr__(self, '_replica_rts', {})   # device index -> runtime of the DataParallel replica on it
 
     # ------------------------------------------------------------------------------------------
     # runtime state (not part of state_dict, not replicated: created lazily per replica/device)
@@ -259,11 +276,24 @@ class SE_UNet(nn.Module):
         def __init__(self):
             self.plans = {}
             self.order = []
-            self.flat = None
-            self.flat_src = None
+            self.flat = None       # flat fp32 copy of the 117 tensors (or the trainer-owned master buffer, see `shared`)
+            self.flat_sig = None   # what `flat` was gathered from: ((data_ptr, _version) per tensor, ext_gen)
+            self.gen = 0           # weight generation: +1 whenever the CONTENTS of `flat` may have changed
+            self.ext_gen = 0       # bumped by whoever updates the parameters behind autograd's back (C-ABI AdamW)
+            self.shared = None     # DataParallelTrainer's master buffer; the module's Parameters are views of it
             self.lock = threading.Lock()
 
     def _runtime(self):
+        """Per-module runtime (plans, flat weights).  nn.DataParallel builds NEW replica objects on every forward, so a
+        replica looks its runtime up by device in a registry shared with the master module: plans and workspaces are
+        then created once per (device, shape), not once per forward (train.py:197, test.py:91, prediction.py:63)."""
+        if self.__dict__.get('_is_replica'):
+            idx = self._param_tensors()[0].device.index
+            reg = self.__dict__['_replica_rts']
+            rt = reg.get(idx)
+            if rt is None:
+                rt = reg.setdefault(idx, SE_UNet._Runtime())
+            return rt
         rt = self.__dict__.get('_rt')
         if rt is None:
             rt = SE_UNet._Runtime()
@@ -274,12 +304,24 @@ class SE_UNet(nn.Module):
         st = super().__getstate__() if hasattr(super(), '__getstate__') else self.__dict__.copy()
         st = dict(st)
         st['_rt'] = None
+        st['_replica_rts'] = {}
         return st
 
+    def __setstate__(self, st):
+        super().__setstate__(st)
+        self.__dict__.setdefault('_rt', None)
+        self.__dict__.setdefault('_replica_rts', {})
+
     def _replicate_for_data_parallel(self):
-        rep = super()._replicate_for_data_parallel()
+        rep = super()._replicate_for_data_parallel()   # shallow __dict__ copy: `_replica_rts` stays the master's dict
         object.__setattr__(rep, '_rt', None)
+        object.__setattr__(rep, '_is_replica', True)
         return rep
+
+    def _params_changed(self):
+        """Tell the module that parameter CONTENTS changed without their version counters moving (in-place update through
+        the C ABI).  The next forward re-gathers the flat copy and re-packs the weight images."""
+        self._runtime().ext_gen += 1
 
     def _param_tensors(self):
         out = []
@@ -290,16 +332,28 @@ class SE_UNet(nn.Module):
             out.append(getattr(m, attr))
         return out
 
-    def _flat_params(self, params):
-        """Flat fp32 copy of the 117 tensors in state_dict order on the compute device.  Re-gathered only
-        when some parameter changed (version counters) or moved."""
+    def _weights(self, params=None):
+        """(flat, gen): flat fp32 buffer of the 117 tensors in state_dict order on the compute device, and its weight
+        generation.  Re-gathered when a parameter was replaced, moved or modified (version counters), or when
+        `_params_changed()` was called; `gen` then advances, which is what `_Plan.pack` compares."""
         rt = self._runtime()
-        src = tuple((p.data_ptr(), p._version) for p in params)
-        if rt.flat is None or rt.flat_src != src or rt.flat.device != params[0].device:
-            with torch.no_grad():
-                rt.flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in params])
-            rt.flat_src = src
-        return rt.flat
+        if params is None:
+            params = self._param_tensors()
+        sig = (tuple((p.data_ptr(), p._version) for p in params), rt.ext_gen)
+        if rt.flat is None or rt.flat_sig != sig or rt.flat.device != params[0].device:
+            shared = rt.shared
+            if shared is not None and _aliases_flat(params, shared):
+                rt.flat = shared    # trainer-owned master buffer: the Parameters ARE views of it, nothing to gather
+            else:
+                rt.shared = None
+                with torch.no_grad():
+                    rt.flat = torch.cat([p.detach().reshape(-1).to(torch.float32) for p in params])
+            rt.flat_sig = sig
+            rt.gen += 1
+        return rt.flat, rt.gen
+
+    def _flat_params(self, params):
+        return self._weights(params)[0]
 
     def _plan(self, batch, D, H, W, mode, device, slot=0):
         """Bound plan for this shape; `slot` selects independent workspaces (concurrent streams)."""
@@ -307,7 +361,8 @@ class SE_UNet(nn.Module):
         key = (batch, D, H, W, self.in_channel, self.n_classes, mode, device.index, slot)
         plan = rt.plans.get(key)
         if plan is None:
-            while len(rt.order) >= _MAX_PLANS:
+            while rt.order and (len(rt.order) >= _MAX_PLANS or
+                                sum(pl.nbytes for pl in rt.plans.values()) > _MAX_PLAN_BYTES):
                 rt.plans.pop(rt.order.pop(0), None)
             plan = _Plan(batch, D, H, W, self.in_channel, self.n_classes, mode, device)
             rt.plans[key] = plan
@@ -331,9 +386,9 @@ class SE_UNet(nn.Module):
         B, _, D, H, W = x.shape
         need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
         with torch.cuda.device(x.device):
-            flat = self._flat_params(params)
+            flat, gen = self._weights(params)
             plan = self._plan(B, D, H, W, 1 if need_grad else 0, x.device)
-            plan.pack(flat)
+            plan.pack(flat, gen)
             drop0 = self.dropout1.scale(B, x.device)   # same RNG draw order as SE_UNet.py:232-233
             drop1 = self.dropout2.scale(B, x.device)
             if need_grad:

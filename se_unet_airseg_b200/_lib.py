@@ -47,8 +47,8 @@ SIGNATURES = {
                                _c.c_float, _i64, _i64, _vp]),
     "seunet_hu_windows": (_i, [_vp, _i, _i64, _c.c_double, _vp, _vp]),
     "seunet_hu_windows_slab": (_i, [_vp, _i, _i64, _i64, _c.c_double, _vp, _vp]),
-    "seunet_window_accumulate": (_i, [_vp, _c.POINTER(_i), _i, _i, _i, _i, _vp, _i, _i, _i, _i, _vp]),
-    "seunet_window_finalize": (_i, [_vp, _vp, _i, _i, _i, _c.c_float, _vp, _i, _vp]),
+    "seunet_window_accumulate": (_i, [_vp, _c.POINTER(_i), _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "seunet_window_finalize": (_i, [_vp, _vp, _i, _i, _i, _c.c_float, _vp, _i, _i, _vp]),
     "seunet_postproc_scratch_bytes": (_sz, [_i, _i, _i, _i64]),
     "seunet_postproc_dti": (_i, [_vp, _i, _i, _i, _c.c_double, _c.c_double, _c.c_double, _vp, _vp, _i64, _vp]),
     "seunet_postproc_largest_component": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i64, _vp]),

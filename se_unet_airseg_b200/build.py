@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libseunet_b200.so")
 STAMP = os.path.join(HERE, ".libseunet_b200.stamp")
 SOURCES = ["conv_tc.cu", "wgrad_tc.cu", "pointwise.cu", "pointwise2.cu", "window.cu", "backward.cu", "backward2.cu", "loss.cu", "postproc.cu", "plan.cu"]  # missing files are skipped
-HEADERS = ["common.cuh", "conv_tc.cuh", "wgrad_tc.cuh", "pointwise.cuh", "backward.cuh", os.path.join("..", "..", "include", "seunet_b200.h")]
+INCLUDE = os.path.join(HERE, "..", "include")
 
 NVCC_FLAGS = [
     "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
@@ -22,12 +22,15 @@ NVCC_FLAGS = [
 
 
 def _source_hash(extra):
+    # every file the translation units can see: all of csrc/ (sources, .cuh headers, the #included .inc schedules) and
+    # include/ - a stale library after editing e.g. plan_bwd.inc would be loaded silently otherwise
     h = hashlib.sha256()
-    for f in SOURCES + HEADERS:
-        p = os.path.join(CSRC, f)
-        if os.path.exists(p):
-            with open(p, "rb") as fh:
-                h.update(fh.read())
+    for d in (CSRC, INCLUDE):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".cu", ".cuh", ".inc", ".h")):
+                h.update(f.encode())
+                with open(os.path.join(d, f), "rb") as fh:
+                    h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS + extra).encode())
     return h.hexdigest()
 

@@ -637,10 +637,14 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
 
 template <int COUT>
 static int conv_launch_t(const ConvLaunch& L, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the dynamic shared-memory limit is a PER-DEVICE function attribute (nn.DataParallel replicas launch on several devices
+  // of one process, one host thread each): remember it per device; a racing duplicate call is harmless
+  static bool attr_set[64] = {};
+  int dev = 0;
+  SEUNET_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     SEUNET_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   conv_tc_kernel<COUT><<<L.grid, kConvThreads, L.g.smem_bytes, st>>>(L.tmap, L.a);
   SEUNET_CUDA_CHECK(cudaGetLastError());

@@ -6,14 +6,20 @@ the reference's prediction.py:65-111:
 
 Differences in HOW (not WHAT): the windows of one resident volume are batched into one forward (the C ABI
 takes per-sample offsets into the volume, no gather copy), probabilities are accumulated on the device in
-fp32 and the window-count volume is analytic; only the final mask crosses PCIe.  Post-processing after the
-threshold (double-threshold iteration, border crop, largest component - prediction.py:110-116) is CPU
-topology code outside this hot path.
+32-bit fixed point (order-independent, see csrc/window.cu) and the window-count volume is analytic; only the
+final mask crosses PCIe.
+
+Multi-GPU (BASELINE config 4): under torchrun the windows of ONE volume are sharded by patch -
+every rank takes a contiguous range of the window list (contiguous slabs along the first axis), accumulates
+into its own partial volume, and one NCCL integer SUM reduce over NVLink merges the partial volumes on rank 0
+(`predict_sharded` / `predict_device_sharded`).  Because the accumulation is integer, the N-rank mask is
+bit-identical to the 1-rank mask.
 """
 import ctypes
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import _lib
 
@@ -33,6 +39,22 @@ def window_starts(length, cube=128, step=64):
             lo = length - cube
         out.append(lo)
     return out
+
+
+def split_batches(n, batch):
+    """Sizes of the forward batches for n windows: ceil(n / batch) batches of (almost) equal size - at most two distinct
+    sizes, so at most two plan shapes per stream slot."""
+    if n <= 0:
+        return []
+    k = -(-n // batch)
+    return [n // k + (1 if i < n % k else 0) for i in range(k)]
+
+
+def shard_range(n, rank, world):
+    """Contiguous range [lo, hi) of the window list owned by `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
 
 
 def coverage_counts(length, starts, cube):
@@ -62,19 +84,29 @@ class SlidingWindowPredictor:
         wins = [(a, b, c) for a in sx for b in sy for c in sz]  # same nesting order as prediction.py:83-100
         counts = np.concatenate([coverage_counts(X, sx, self.cube), coverage_counts(Y, sy, self.cube),
                                  coverage_counts(Z, sz, self.cube)]).astype(np.int32)
-        g = dict(wins=wins, counts=torch.from_numpy(counts).to(device),
-                 acc=torch.empty((X, Y, Z), dtype=torch.float32, device=device),
+        cmax = int(coverage_counts(X, sx, self.cube).max()) * int(coverage_counts(Y, sy, self.cube).max()) * \
+            int(coverage_counts(Z, sz, self.cube).max())
+        acc_log2 = min(26, 30 - int(np.ceil(np.log2(cmax + 1))))      # cmax * 2^acc_log2 < 2^31 (NCCL sums it as int32)
+        if acc_log2 < 16:
+            raise ValueError(f"window grid overlaps {cmax} times per voxel: too dense for the fixed-point accumulator")
+        g = dict(wins=wins, counts=torch.from_numpy(counts).to(device), acc_log2=acc_log2,
+                 acc=torch.empty((X, Y, Z), dtype=torch.int32, device=device),
                  mask=torch.empty((X, Y, Z), dtype=torch.uint8, device=device),
                  x2=torch.empty((1, 2, X, Y, Z), dtype=torch.float32, device=device))
         self._geom = ((tuple(shape), device), g)
         return g
 
     @torch.no_grad()
-    def predict_device(self, img_dev, hu_offset=-1024.0, return_prob=False, _slab_events=None):
+    def predict_device(self, img_dev, hu_offset=-1024.0, return_prob=False, reuse_output=False, _slab_events=None,
+                       _shard=None):
         """img_dev: (X, Y, Z) int16 or fp32 CUDA tensor holding the stored CT values (HU + 1024, prediction.py:68-69).
         Returns the uint8 mask (X, Y, Z) on the device (and the mean probability if return_prob).
+        The results are fresh tensors unless reuse_output=True, which hands out the predictor's own accumulator / mask
+        buffers: they are OVERWRITTEN by the next call on a volume of the same shape (zero-copy mode for streaming use).
         _slab_events (internal, used by predict()): [(x_end, event)] - the two-HU-window input has already been produced slab
-        by slab on a copy stream; a window batch waits only for the slabs it reads."""
+        by slab on a copy stream; a window batch waits only for the slabs it reads.
+        _shard (internal, used by the *_sharded entry points): (rank, world, group) - run only this rank's range of the
+        window list and merge the partial volumes with one integer SUM reduce to rank 0; ranks != 0 return None."""
         L = _lib.lib()
         m = self.model
         if m.in_channel != 2:
@@ -95,8 +127,11 @@ class SlidingWindowPredictor:
         sN, sC, sD, sH, sW = x2.stride()
         cube = self.cube
         wins = g["wins"]
+        if _shard is not None:
+            lo, hi = shard_range(len(wins), _shard[0], _shard[1])
+            wins = wins[lo:hi]
         params = m._param_tensors()
-        flat = m._flat_params(params)
+        flat, wgen = m._weights(params)
         main = torch.cuda.current_stream(dev)
         if self._streams is None or self._streams[0].device != dev:
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(self.nstreams)] if self.nstreams > 1 else [main]
@@ -106,9 +141,8 @@ class SlidingWindowPredictor:
             ready.record(main)
             for s_ in streams:
                 s_.wait_event(ready)
-        i, k = 0, 0
-        while i < len(wins):
-            b = min(self.batch, len(wins) - i)
+        i = 0
+        for k, b in enumerate(split_batches(len(wins), self.batch)):
             slot = k % len(streams)
             cs = streams[slot]
             if _slab_events is not None:
@@ -120,7 +154,7 @@ class SlidingWindowPredictor:
             with torch.cuda.stream(cs):
                 stp = ctypes.c_void_p(cs.cuda_stream)
                 plan = m._plan(b, cube, cube, cube, 0, dev, slot=slot)
-                plan.pack(flat)
+                plan.pack(flat, wgen)
                 ones0, ones1, pred0, pred1 = self._buffers(plan, b, dev)
                 offs = (ctypes.c_int64 * b)(*[w[0] * sD + w[1] * sH + w[2] * sW for w in wins[i:i + b]])
                 strides = (ctypes.c_int64 * 5)(0, sC, sD, sH, sW)
@@ -128,24 +162,63 @@ class SlidingWindowPredictor:
                                             _lib.ptr(ones1), _lib.ptr(pred0), _lib.ptr(pred1), stp), "seunet_forward")
                 starts = (ctypes.c_int * (3 * b))(*[v for w in wins[i:i + b] for v in w])
                 _lib.check(L.seunet_window_accumulate(_lib.ptr(pred1), starts, b, cube, cube, cube, _lib.ptr(g["acc"]),
-                                                      X, Y, Z, 1, stp), "seunet_window_accumulate")
+                                                      X, Y, Z, 1, g["acc_log2"], stp), "seunet_window_accumulate")
             i += b
-            k += 1
         if self.nstreams > 1:
             for s_ in streams:
                 done = torch.cuda.Event()
                 done.record(s_)
                 main.wait_event(done)
+        if _shard is not None and _shard[1] > 1:
+            # the one exchange step of patch sharding: partial fixed-point volumes -> rank 0 (NCCL over NVLink/NVSwitch)
+            dist.reduce(g["acc"], dst=dist.get_global_rank(_shard[2], 0) if _shard[2] is not None else 0,
+                        op=dist.ReduceOp.SUM, group=_shard[2])
+            if _shard[0] != 0:
+                return None
         _lib.check(L.seunet_window_finalize(_lib.ptr(g["acc"]), _lib.ptr(g["counts"]), X, Y, Z, float(self.threshold),
-                                            _lib.ptr(g["mask"]), 1 if return_prob else 0, st), "seunet_window_finalize")
-        return (g["mask"], g["acc"]) if return_prob else g["mask"]
+                                            _lib.ptr(g["mask"]), 1 if return_prob else 0, g["acc_log2"], st),
+                   "seunet_window_finalize")
+        prob = g["acc"].view(torch.float32)     # finalize(write_mean) replaced the fixed-point sums by the fp32 means
+        if reuse_output:
+            return (g["mask"], prob) if return_prob else g["mask"]
+        return (g["mask"].clone(), prob.clone()) if return_prob else g["mask"].clone()
+
+    # ------------------------------------------------------------------------------------------
+    # patch-sharded inference of one volume over the ranks of a process group (one process per GPU)
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _shard_info(group):
+        if not dist.is_initialized():
+            return (0, 1, group)
+        return (dist.get_rank(group), dist.get_world_size(group), group)
+
+    def shard_planes(self, shape, rank, world):
+        """[x_lo, x_hi): planes along the first axis that `rank`'s windows read (what it needs on its device)."""
+        sx, sy, sz = (window_starts(n, self.cube, self.step) for n in shape)
+        wins = [(a, b, c) for a in sx for b in sy for c in sz]
+        lo, hi = shard_range(len(wins), rank, world)
+        if lo == hi:
+            return 0, 0
+        return min(w[0] for w in wins[lo:hi]), max(w[0] for w in wins[lo:hi]) + self.cube
+
+    @torch.no_grad()
+    def predict_device_sharded(self, img_dev, hu_offset=-1024.0, return_prob=False, reuse_output=False, group=None):
+        """Collective call (every rank of `group`): img_dev is this rank's device copy of the stored CT volume - only the
+        planes of `shard_planes()` are read.  Rank 0 returns the mask (and mean probability), the others None."""
+        return self.predict_device(img_dev, hu_offset, return_prob, reuse_output, _shard=self._shard_info(group))
+
+    @torch.no_grad()
+    def predict_sharded(self, img_host, hu_offset=-1024.0, slab=64, reuse_output=False, group=None):
+        """Collective end-to-end call: every rank passes the same host volume (e.g. the memory-mapped NIfTI the ranks of
+        one node share); each rank copies only the planes its windows read, rank 0 returns the host mask."""
+        return self.predict(img_host, hu_offset, slab, reuse_output, _shard=self._shard_info(group))
 
     @torch.no_grad()
     def predict_postprocessed_device(self, img_dev, hu_offset=-1024.0, h_thresh=0.5, l_thresh=0.4, border_frac=0.15):
         """The whole of prediction.py:78-116 on the device: sliding-window mean probability, double-threshold hysteresis,
         border crop, largest 26-connected component, hole filling.  Returns the final uint8 mask (X, Y, Z)."""
         from .postprocess import PostProcessor
-        _, prob = self.predict_device(img_dev, hu_offset, return_prob=True)
+        _, prob = self.predict_device(img_dev, hu_offset, return_prob=True, reuse_output=True)   # consumed before returning
         pp = getattr(self, "_post", None)
         if pp is None or (pp.D, pp.H, pp.W) != tuple(prob.shape) or pp.device != prob.device:
             pp = PostProcessor(tuple(prob.shape), prob.device)
@@ -163,11 +236,14 @@ class SlidingWindowPredictor:
         return buf
 
     @torch.no_grad()
-    def predict(self, img_host, hu_offset=-1024.0, slab=64):
+    def predict(self, img_host, hu_offset=-1024.0, slab=64, reuse_output=False, _shard=None):
         """End-to-end call a user makes: host volume (numpy int16/float32 or CPU tensor, ideally pinned) in, host uint8
         mask out.  The H2D copy and the HU windowing run slab by slab (along the first axis) on a copy stream, and every window
         batch waits only for the slabs it reads, so the forward passes start after the first ~128 planes have arrived;
-        one D2H copy of the mask at the end."""
+        one D2H copy of the mask at the end.
+        Returns a fresh CPU tensor.  reuse_output=True returns the predictor's pinned staging buffer instead (no host
+        copy); it is OVERWRITTEN by the next predict() of a same-shaped volume - only for callers that consume the mask
+        before the next call (prediction.py does: it writes the NIfTI, then moves on)."""
         L = _lib.lib()
         t = torch.from_numpy(img_host) if isinstance(img_host, np.ndarray) else img_host
         dev = next(p for p in self.model._param_tensors()).device
@@ -191,9 +267,10 @@ class SlidingWindowPredictor:
         copy_stream.wait_event(start)
         events = []
         plane = Y * Z
+        xa, xb = (0, X) if _shard is None else self.shard_planes((X, Y, Z), _shard[0], _shard[1])
         with torch.cuda.stream(copy_stream):
-            for x0 in range(0, X, slab):
-                x1 = min(X, x0 + slab)
+            for x0 in range(xa, xb, slab):
+                x1 = min(xb, x0 + slab)
                 stage[x0:x1].copy_(t[x0:x1], non_blocking=True)
                 _lib.check(L.seunet_hu_windows_slab(_lib.ptr(stage[x0:x1]), dtype, (x1 - x0) * plane, X * plane, float(hu_offset),
                                                     ctypes.c_void_p(g["x2"].data_ptr() + x0 * plane * 4),
@@ -201,11 +278,14 @@ class SlidingWindowPredictor:
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 events.append((x1, ev))
-        mask = self.predict_device(stage, hu_offset, _slab_events=events)
+        mask = self.predict_device(stage, hu_offset, reuse_output=True, _slab_events=events, _shard=_shard)
+        if mask is None:            # sharded call on a rank != 0
+            torch.cuda.current_stream(dev).synchronize()
+            return None
         out = getattr(self, "_host_mask", None)
         if out is None or out.shape != mask.shape:
             out = torch.empty(mask.shape, dtype=torch.uint8, pin_memory=True)
             self._host_mask = out
         out.copy_(mask, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        return out
+        return out if reuse_output else out.clone()

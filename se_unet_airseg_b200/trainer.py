@@ -45,14 +45,7 @@ class DataParallelTrainer:
         self.device = params[0].device
         if self.device.type != "cuda":
             raise _lib.SeunetError("DataParallelTrainer needs the model on a CUDA device")
-        # one flat fp32 master copy; the module's Parameters become views of it so state_dict()/checkpoints stay live
-        with torch.no_grad():
-            self.flat = torch.cat([p.detach().reshape(-1).float() for p in params]).contiguous()
-            off = 0
-            for p in params:
-                n = p.numel()
-                p.data = self.flat[off:off + n].view(p.shape)
-                off += n
+        self._adopt(params)
         self.grads = torch.zeros_like(self.flat)
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
@@ -63,6 +56,32 @@ class DataParallelTrainer:
         self.skip_off = L.seunet_param_offset(ic, nc, b"dc62.conv1.weight")
         self.skip_len = 48 * 16
         self._buf = None
+
+    def _adopt(self, params):
+        """One flat fp32 master copy; the module's Parameters become views of it so state_dict()/checkpoints stay live and
+        the fused AdamW updates them in place.  The buffer is registered with the module's runtime (`shared`): eval-mode
+        forwards and the sliding-window predictor then read the SAME memory, and `model._params_changed()` after every step
+        advances the weight generation that guards the packed tensor-core images."""
+        with torch.no_grad():
+            flat = torch.cat([p.detach().reshape(-1).float() for p in params]).contiguous()
+            off = 0
+            for p in params:
+                n = p.numel()
+                p.data = flat[off:off + n].view(p.shape)
+                off += n
+        self.flat = flat
+        rt = self.model._runtime()
+        rt.shared = flat
+        rt.flat = None      # force the next _weights() to re-resolve
+
+    def _check_input(self, name, t, shape):
+        if t is None:
+            return None
+        if not torch.is_tensor(t) or t.device != self.device:
+            raise ValueError(f"{name}: expected a tensor on {self.device}, got {getattr(t, 'device', type(t))}")
+        if tuple(t.shape) != shape:
+            raise ValueError(f"{name}: expected shape {shape}, got {tuple(t.shape)}")
+        return t.to(torch.float32).contiguous()   # no-ops for the fp32 contiguous tensors the loaders produce
 
     def _buffers(self, shape):
         if self._buf is None or self._buf[0] != shape:
@@ -76,11 +95,28 @@ class DataParallelTrainer:
         (no host synchronisation).  x: (B, in_ch, D, H, W) fp32 CUDA; label/weight/skel: (B, 1, D, H, W) fp32 CUDA."""
         L = _lib.lib()
         m = self.model
+        if not torch.is_tensor(x) or x.dim() != 5 or x.shape[1] != m.in_channel or x.device != self.device:
+            raise ValueError(f"x: expected (B, {m.in_channel}, D, H, W) on {self.device}, got "
+                             f"{tuple(x.shape) if torch.is_tensor(x) else type(x)}")
+        if x.dtype != torch.float32:
+            x = x.float()
         B, _, D, H, W = x.shape
+        label = self._check_input("label", label, (B, 1, D, H, W))
+        weight = self._check_input("weight", weight, (B, 1, D, H, W))
+        skel = self._check_input("skel", skel, (B, 1, D, H, W))
+        if label is None or (self.stage >= 2 and weight is None) or (self.stage == 3 and skel is None):
+            raise ValueError(f"stage {self.stage} needs label" + (", weight" if self.stage >= 2 else "") +
+                             (", skel" if self.stage == 3 else ""))
         st = _lib.stream_ptr()
         with torch.cuda.device(self.device), torch.no_grad():
+            params = m._param_tensors()
+            flat, wgen = m._weights(params)     # notices load_state_dict / external edits through the version counters
+            if flat is not self.flat:           # parameters were re-created or moved: adopt the new tensors
+                self._adopt(params)
+                self.m.zero_(); self.v.zero_(); self.step_count = 0
+                flat, wgen = m._weights(params)
             plan = m._plan(B, D, H, W, 1, self.device)
-            plan.pack(self.flat)
+            plan.pack(self.flat, wgen)
             plan.generation += 1
             drop0 = m.dropout1.scale(B, self.device)
             drop1 = m.dropout2.scale(B, self.device)
@@ -105,6 +141,6 @@ class DataParallelTrainer:
             _lib.check(L.seunet_adamw_step(p_(self.flat), p_(self.grads), p_(self.m), p_(self.v), self.flat.numel(), hp["lr"],
                                            hp["betas"][0], hp["betas"][1], hp["eps"], hp["weight_decay"], self.step_count, 1.0,
                                            self.skip_off, self.skip_len, st), "seunet_adamw_step")
-            self.flat.add_(0)   # bump the version counter: the in-place C-ABI update is invisible to autograd's bookkeeping
+            m._params_changed()   # the in-place C-ABI update is invisible to the tensors' version counters
         self.per_sample_gul = per_sample
         return self.loss

@@ -54,7 +54,9 @@ def test_full_size_volume_properties():
     """BASELINE config-2 size (512x512x400, 294 windows of 128^3).  The CPU oracle would need ~7 minutes, so the whole-volume
     path is checked through size-independent properties: (a) the corner block that only ONE window covers equals that
     window's own sigmoid output; (b) a block covered by 8 windows equals the mean of those 8 window outputs; (c) the result does
-    not depend on the window batch / stream configuration beyond fp32 summation order; (d) mask == (mean probability >= 0.5)."""
+    not depend on the window batch / stream configuration (the fixed-point accumulation is exactly order-independent;
+    the per-window forward is batch-invariant up to the order of the fp64 InstanceNorm-statistics atomics); (d) mask == (mean probability >= 0.5).  The comparison of the whole volume against the fp32 oracle
+    lives in tests/test_gpu_full_volume.py."""
     from se_unet_airseg_b200 import SE_UNet
     from se_unet_airseg_b200.inference import SlidingWindowPredictor
     sd = oracle.init_params(2, 1, seed=777)
@@ -84,4 +86,5 @@ def test_full_size_volume_properties():
     assert (prob[64:128, 64:128, 64:128] - acc / 8).abs().max().item() <= 1e-5
     sw2 = SlidingWindowPredictor(m, batch=3, streams=1)
     _, prob2 = sw2.predict_device(img, return_prob=True)
-    assert (prob2 - prob).abs().max().item() <= 1e-5
+    assert (prob2 - prob).abs().max().item() <= 1e-6
+    assert (mask != (prob2 >= 0.5)).sum().item() <= 2
