@@ -152,9 +152,126 @@ def main_postproc():
         print(name, "set voxels", int(ref.sum()), "strong", int((p >= 0.5).sum()))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# maximum_3d (util.py:58-75).  The function's TEXT is the reference's own (extracted with ast, executed unmodified); the two
+# third-party calls it makes are not installed in this container (connected-components-3d 3.x `cc3d.connected_components`,
+# scikit-image `measure.regionprops`), so they are supplied by the two small stand-ins below, which restate the published
+# behaviour of exactly the features the call sites use and are validated against an independent implementation
+# (scipy.ndimage.label with the full 3x3x3 structure) before any fixture is written:
+#   cc3d.connected_components(binary, connectivity=26): 26-connected components of the non-zero voxels, labels 1..N numbered
+#     in raster order (C order for a C-contiguous array) of each component's first voxel;
+#   measure.regionprops(label): one entry per label in ascending label order, `.area` = voxel count.
+# ---------------------------------------------------------------------------------------------------------------------
+class _CC3DStandIn:
+    @staticmethod
+    def connected_components(region, connectivity=26):
+        assert connectivity == 26
+        a = np.asarray(region) != 0
+        lab = np.zeros(a.shape, dtype=np.uint32)
+        nxt = 0
+        D, H, W = a.shape
+        for i in range(D):
+            for j in range(H):
+                for k in range(W):
+                    if a[i, j, k] and lab[i, j, k] == 0:        # first voxel of a new component in raster order
+                        nxt += 1
+                        lab[i, j, k] = nxt
+                        stack = [(i, j, k)]
+                        while stack:
+                            x, y, z = stack.pop()
+                            for u in range(max(x - 1, 0), min(x + 2, D)):
+                                for v in range(max(y - 1, 0), min(y + 2, H)):
+                                    for w in range(max(z - 1, 0), min(z + 2, W)):
+                                        if a[u, v, w] and lab[u, v, w] == 0:
+                                            lab[u, v, w] = nxt
+                                            stack.append((u, v, w))
+        return lab
+
+
+class _RegionPropsStandIn:
+    class _R:
+        def __init__(self, area):
+            self.area = area
+
+    @staticmethod
+    def regionprops(label):
+        cnt = np.bincount(np.asarray(label).ravel())
+        return [_RegionPropsStandIn._R(int(c)) for c in cnt[1:] if c > 0]
+
+
+def load_reference_maximum_3d():
+    from scipy.ndimage import binary_fill_holes
+    src = open(os.path.join(REF, "util.py")).read()
+    ns = {"np": np, "cc3d": _CC3DStandIn, "measure": _RegionPropsStandIn, "binary_fill_holes": binary_fill_holes}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == "maximum_3d":
+            exec(compile(ast.Module([node], []), "util.py", "exec"), ns)
+    return ns["maximum_3d"]
+
+
+def max3d_cases():
+    """(name, binary int8 volume): random blobs, an exact AREA TIE (the reversed stable sort picks the later label), the
+    probe-slice fallback (largest component misses the slices W//2, W//3, W//3*2 of the last axis), diagonal (26- but not
+    6-/18-) connectivity, enclosed holes."""
+    from scipy import ndimage
+    out = []
+    for seed, shape, thr in ((1, (14, 16, 30), 0.58), (2, (10, 12, 41), 0.62), (3, (20, 9, 24), 0.55)):
+        rng = np.random.RandomState(seed)
+        f = ndimage.gaussian_filter(rng.rand(*shape), 1.0)
+        f = (f - f.min()) / (f.max() - f.min())
+        out.append((f"blobs{seed}", (f > thr).astype(np.int8)))
+    tie = np.zeros((8, 8, 12), dtype=np.int8)
+    tie[1:3, 1:3, 5:8] = 1            # 12 voxels, label 1 (first in raster order), touches slice 6 = 12 // 2
+    tie[5:7, 5:7, 4:7] = 1            # 12 voxels, label 2 -> wins the tie
+    tie[4, 0, 0] = 1                  # a 1-voxel component
+    out.append(("tie", tie))
+    probe = np.zeros((9, 9, 30), dtype=np.int8)
+    probe[1:8, 1:8, 0:4] = 1          # largest (196 voxels) but away from slices 15, 10, 20
+    probe[3:6, 3:6, 9:22] = 1         # second largest, crosses all three probe slices
+    probe[0, 0, 28] = 1
+    out.append(("probe", probe))
+    diag = np.zeros((7, 7, 9), dtype=np.int8)
+    for t in range(6):
+        diag[t, t, t + 1] = 1         # corner-connected chain: one component only under 26-connectivity
+    diag[5:7, 0:2, 3:6] = 1
+    out.append(("diag", diag))
+    hole = np.zeros((9, 9, 9), dtype=np.int8)
+    hole[1:8, 1:8, 1:8] = 1
+    hole[3:6, 3:6, 3:6] = 0           # enclosed cavity: filled by binary_fill_holes
+    hole[4, 4, 4] = 1                 # an island inside the cavity (a separate, smaller component)
+    out.append(("hole", hole))
+    return out
+
+
+def main_max3d():
+    from scipy import ndimage
+    # validate the stand-in against an independent implementation, numbering included
+    for seed in range(6):
+        rng = np.random.RandomState(100 + seed)
+        a = (rng.rand(9, 11, 13) > 0.72).astype(np.int8)
+        mine = _CC3DStandIn.connected_components(a, connectivity=26)
+        ref, n = ndimage.label(a, structure=np.ones((3, 3, 3)))
+        assert n == mine.max() and np.array_equal(mine.astype(np.int64), ref.astype(np.int64)), "cc3d stand-in is not faithful"
+        areas = [r.area for r in _RegionPropsStandIn.regionprops(mine)]
+        assert areas == [int((ref == i).sum()) for i in range(1, n + 1)]
+    fn = load_reference_maximum_3d()
+    data = {}
+    for name, vol in max3d_cases():
+        ref = np.asarray(fn(vol.copy())).astype(np.uint8)
+        mine = oracle.maximum_3d(vol).astype(np.uint8)
+        assert np.array_equal(ref, mine), f"oracle.maximum_3d differs from the reference's function on case {name}"
+        data["in." + name] = vol
+        data["out." + name] = ref
+        print("max3d", name, vol.shape, "in", int(vol.sum()), "out", int(ref.sum()))
+    np.savez_compressed(os.path.join(OUT, "postproc_max3d.npz"), **data)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "postproc":
         main_postproc()
+    elif len(sys.argv) > 1 and sys.argv[1] == "max3d":
+        main_max3d()
     else:
         main()
         main_postproc()
+        main_max3d()

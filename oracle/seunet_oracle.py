@@ -322,10 +322,13 @@ def two_channel(img_hu):
 
 def predict_volume(sd, img_stored, cube=128, step=64):
     """prediction.py:65-111 up to the 0.5 threshold: img_stored holds the stored CT values (HU + 1024);
-    returns (mean probability float64 volume, mask).  Eval mode like prediction.py:64."""
+    returns (mean probability float64 volume, mask).  Eval mode like prediction.py:64.  The forward runs on the device of
+    the parameter tensors (the full-size GPU parity test puts them on the B200 in fp32 with TF32 disabled); the overlap
+    accumulation is the reference's host float64 `+=` either way (prediction.py:104-107)."""
     import numpy as np
-    img = img_stored.to(torch.float64) - 1024                                       # :69
+    img = img_stored.cpu().to(torch.float64) - 1024                                 # :69
     x = two_channel(img).to(torch.float32).unsqueeze(0)                            # :72-77
+    x = x.to(next(iter(sd.values())).device)                                        # :75-77 (.cuda())
     X, Y, Z = img.shape
     pred = np.zeros((X, Y, Z))
     pred_num = np.zeros((X, Y, Z))
@@ -334,7 +337,7 @@ def predict_volume(sd, img_stored, cube=128, step=64):
             for yl in window_starts(Y, cube, step):
                 for zl in window_starts(Z, cube, step):
                     _p0, p = forward(sd, x[:, :, xl:xl + cube, yl:yl + cube, zl:zl + cube])   # :102-103
-                    p = torch.sigmoid(p).numpy()[0, 0]                             # :104-105
+                    p = torch.sigmoid(p).cpu().numpy()[0, 0]                       # :104-105
                     pred[xl:xl + cube, yl:yl + cube, zl:zl + cube] += p            # :106
                     pred_num[xl:xl + cube, yl:yl + cube, zl:zl + cube] += 1        # :107
     pred = pred / pred_num                                                         # :109

@@ -17,8 +17,9 @@
 //     adjacently (for dil=2 the even planes first, then the odd ones), so one instruction with
 //     N = 3*Cout feeds three accumulators.  This triples the reuse of the A tile read from shared
 //     memory, which is what limits small-N UMMA shapes.
-//   * A CTA tile is DT = 256/Cout output planes of one 16x8 patch; two TMEM accumulator stages
-//     (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//   * A CTA tile is DT = 512/Cout output planes of one 16x8 patch: the whole TMEM is one accumulator stage whose
+//     plane slots are handed back and forth individually (per-slot mbarriers), so the epilogue of tile i still
+//     overlaps the MMAs of tile i+1 (see the comment above the kernel).
 //   * Weights are pre-packed into the exact shared-memory image ([chunk][step][khalf][3*Cout][8]) and
 //     either stay resident for the whole (persistent) CTA or stream through a 2-slot ring when
 //     27*Cin*Cout*2 B does not fit (Cin*Cout >= 64*64).
@@ -48,35 +49,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKArgs& a, int tile) {
   t.Dp = a.dstep == 2 ? ((a.D - t.par + 1) >> 1) : a.D;
   t.n = tile; t.d0 = td * DT; t.h0 = th * kConvTileH; t.w0 = tw * kConvTileW;
   return t;
-}
-
-// accumulator slot of output plane p_rel (tile-relative): planes that share one input plane must be
-// adjacent, i.e. for dilation 2 the even planes come first, then the odd ones.
-template <int DT>
-__device__ __forceinline__ int plane_slot(int p_rel, int dil) {
-  return dil == 2 ? ((p_rel & 1) * (DT / 2) + (p_rel >> 1)) : p_rel;
-}
-template <int DT>
-__device__ __forceinline__ int slot_plane(int slot, int dil) {
-  return dil == 2 ? ((slot % (DT / 2)) * 2 + slot / (DT / 2)) : slot;
-}
-
-// Stacked kd blocks (j=0 -> kd=2 -> output plane q-dil, j=1 -> q, j=2 -> q+dil) that are valid for the tile-relative
-// input plane q_rel: first block jlo, count nj (valid blocks are always contiguous), first output plane p_lo.
-// dteff = number of valid output planes of this tile.  Returns false when the plane is not needed at all.
-__device__ __forceinline__ bool plane_blocks(int nkd, int dil, int D, int d0, int dteff, int q_rel, int& jlo, int& nj, int& p_lo) {
-  const int q = d0 + q_rel;
-  if (q < 0 || q >= D) return false;
-  if (nkd == 1) {
-    jlo = 0; nj = 1; p_lo = q_rel;
-    return q_rel < dteff;
-  }
-  const int p0 = q_rel - dil, p2 = q_rel + dil;
-  const int v0 = (p0 >= 0) & (p0 < dteff), v1 = (q_rel >= 0) & (q_rel < dteff), v2 = (p2 >= 0) & (p2 < dteff);
-  nj = v0 + v1 + v2;
-  jlo = v0 ? 0 : (v1 ? 1 : 2);
-  p_lo = q_rel + (jlo - 1) * dil;
-  return nj != 0;
 }
 
 // The 9 in-plane taps x J 16-channel blocks of one input plane, fully unrolled (J = 0: runtime block count).  Runs on
@@ -113,11 +85,24 @@ __device__ __forceinline__ void issue_taps3(uint32_t dcol, uint32_t a_lo_st, uin
   }
 }
 
+// Accumulator organisation (round 2).  The whole TMEM (512 columns) is ONE stage of DT = 512/COUT output-plane slots, and
+// every slot has its own full/empty mbarrier pair:
+//   * the issuer acquires slot p (waits for "empty": drained AND zeroed by the epilogue) right before the first input
+//     plane that touches output plane p, accumulates unconditionally, and commits "full" for p right after the last input
+//     plane that touches it (input p + dil, last channel chunk);
+//   * the epilogue drains the slots in plane order as they complete: tcgen05.ld, then tcgen05.st of zeros (off the tensor
+//     pipe), arrive "empty", and only then the conversions / global stores / statistics.
+// The next tile starts on slot 0 while the last slots of the previous tile are still being drained, so the epilogue is
+// hidden exactly as with two half-size stages, but a tile is twice as deep: (DT + 2)/DT input planes per output plane
+// instead of (DT/2 + 2)/(DT/2) - 1.25 instead of 1.5 for COUT = 64, 1.125 instead of 1.25 for COUT = 32.
 template <int COUT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvKArgs a) {
   constexpr int DT = kConvAccCols / COUT;
-  __shared__ float s_run[4][COUT / 16][32];   // per-epilogue-warp running InstanceNorm partial sums
+  constexpr int NCG = COUT / 16;
+  // per-epilogue-warp running InstanceNorm partial sums.  fp64: the per-tile fp32 partials are a fixed function of the
+  // tile, so the statistics do not depend on which tiles a CTA happens to process (batch size, grid) beyond fp64 rounding.
+  __shared__ double s_run[4][NCG][32];
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // dynamic smem base is only guaranteed 16-byte aligned: align to 128 by hand
   const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -131,9 +116,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   auto wfull_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + i); };
   auto wempty_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 8 + i); };
   auto tfull_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 16 + i); };
-  auto tempty_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 18 + i); };
-  const uint32_t tmem_slot_addr = bar_addr + 8u * (2 * kConvMaxStages + 20);
-  const uint32_t zero_addr = bar_addr + 8u * (2 * kConvMaxStages + 32);   // 128 zero bytes: operands of the accumulator-clearing UMMA
+  auto tempty_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 48 + i); };
+  const uint32_t tmem_slot_addr = bar_addr + 8u * (2 * kConvMaxStages + 80);
 
   // warp index through a shuffle so that the compiler KNOWS it is warp-uniform: the role branches and everything
   // inside them (loop counters, descriptors) can then live in uniform registers, which UTCHMMA needs anyway.
@@ -143,12 +127,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.nstages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
     for (int i = 0; i < a.wslots; ++i) { mbar_init(wfull_bar(i), 1); mbar_init(wempty_bar(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    for (int i = 0; i < DT; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
     fence_mbar_init();
     tma_prefetch_desc(&tmap);
   }
-  if (threadIdx.x < 32) asm volatile("st.shared.u32 [%0], %1;" ::"r"(zero_addr + 4u * threadIdx.x), "r"(0u) : "memory");
-  fence_proxy_async();   // generic-proxy zeros must be visible to the tensor core (async proxy)
   if (warp == 1) {
     tmem_alloc(tmem_slot_addr, 512);
     tmem_relinquish();
@@ -161,7 +143,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   const bool resident = a.nchunks <= a.wslots;
-  const int nq = DT + 2 * a.dil;  // candidate input planes per tile (dil == 0 for pointwise)
 
   if (warp == 0) {
     // =================================== TMA producer ===================================
@@ -180,6 +161,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         for (int c = 0; c < a.nchunks; ++c) load_weights(c, c);
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<DT>(a, tile);
+        const int dteff = min(DT, t.Dp - t.d0);
+        const int q_begin = max(-a.dil, -t.d0), q_end = min(dteff + a.dil, t.Dp - t.d0);   // same range as the issuer
         for (int c = 0; c < a.nchunks; ++c) {
           if (!resident) {
             const int slot = wcount % a.wslots;
@@ -188,10 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             load_weights(c, slot);
             ++wcount;
           }
-          for (int qi = 0; qi < nq; ++qi) {
-            int jlo, nj, p_lo;
-            const int q_rel = qi - a.dil;
-            if (!plane_blocks(a.nkd, a.dil, t.Dp, t.d0, min(DT, t.Dp - t.d0), q_rel, jlo, nj, p_lo)) continue;
+          for (int q_rel = q_begin; q_rel < q_end; ++q_rel) {
             mbar_wait(empty_bar(st), ph ^ 1u);
             mbar_expect_tx(full_bar(st), a.box_bytes);
             tma_load_4d(s_addr + st * a.stage_bytes, &tmap, full_bar(st),
@@ -207,11 +187,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     // The whole warp runs this loop with warp-uniform control flow so that descriptors live in
     // uniform registers; only the tcgen05.mma / tcgen05.commit themselves are issued by one elected lane.
     {
-      uint32_t st = 0, ph = 0, wcount = 0, acc = 0, accph = 0, wready = 0;
+      uint32_t st = 0, ph = 0, wcount = 0, wready = 0;
+      uint32_t use_bits = 0;                  // bit p: parity of the number of completed uses of accumulator slot p
       const uint32_t idesc1 = umma_idesc(a.fmt, 128, COUT);
       constexpr uint32_t kIdescNStep = (uint32_t)(COUT >> 3) << 17;   // one more kd block along N
-      const uint32_t idesc_clear = umma_idesc(a.fmt, 128, kConvAccCols);
-      const uint64_t zdesc = umma_desc(zero_addr, 0, 0);   // every core matrix reads the same 128 zero bytes
       const int dil = a.dil, nkd = a.nkd;
       const uint32_t a_hi = a.a_hi, b_hi = a.b_hi, stage16 = a.stage16;
       const uint32_t a_lo_first = a.a_lo0 | ((s_addr & 0x3FFFFu) >> 4);
@@ -222,16 +201,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       // bit mask instead of the count, so that the dispatch below compiles to uniform branches and not to a jump table
       const int jmode = jsteps == 1 ? 1 : (jsteps == 2 ? 2 : (jsteps == 4 ? 4 : 8));
       const uint32_t kh_step = a.kh_step, kw_step = a.kw_step, j_step = a.j_step, b_step = a.b_step;
+      const int last_chunk = a.nchunks - 1;
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<DT>(a, tile);
         const int D = t.Dp;
         const int dteff = min(DT, D - t.d0);
-        mbar_wait(tempty_bar(acc), accph ^ 1u);
-        tc_fence_after();
-        const uint32_t dstage = tmem_base + acc * kConvAccCols;
-        // Clear the whole accumulator stage with one UMMA (D = 0 x 0, accumulate off).  Every later instruction then
-        // accumulates unconditionally, so the kd-stacked accumulators need no first-touch bookkeeping.
-        if (elect_one_sync()) umma_f16(dstage, zdesc, zdesc, idesc_clear, 0u);
+        // input planes q_rel in [-dil, dteff + dil) that exist in the volume
+        const int q_begin = max(-dil, -t.d0), q_end = min(dteff + dil, D - t.d0);
+        int next_fresh = 0, next_done = 0;    // output planes not yet acquired / not yet committed
         for (int c = 0; c < a.nchunks; ++c) {
           int slot;
           if (resident) {
@@ -242,8 +219,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             mbar_wait(wfull_bar(slot), (wcount / a.wslots) & 1u);
           }
           const uint32_t b_lo_slot = b_lo_lbo | (((w_addr + slot * a.wchunk_bytes) & 0x3FFFFu) >> 4);
-          // input planes q_rel in [-dil, DT + dil) that exist in the volume
-          const int q_begin = max(-dil, -t.d0), q_end = min(DT + dil, D - t.d0);
           for (int q_rel = q_begin; q_rel < q_end; ++q_rel) {
             // kd block j (j = 0,1,2) of this input plane feeds output plane q_rel + (j-1)*dil; the valid ones are contiguous
             int jlo = 0, nj = 1, p_lo = q_rel;
@@ -252,11 +227,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               jlo = (p0 < 0) + (q_rel < 0);                                   // p2 >= 0 always holds here
               nj = (p0 < dteff) + (q_rel < dteff) + (p2 < dteff) - jlo;
               p_lo = q_rel + (jlo - 1) * dil;
-            } else if (q_rel >= dteff) {
-              nj = 0;
             }
-            if (nj <= 0) continue;
-            const uint32_t dcol = dstage + plane_slot<DT>(p_lo, dil) * COUT;
+            if (c == 0) {
+              // first touch of output planes <= p_hi: their slots must have been drained and zeroed by the epilogue
+              const int p_hi = p_lo + nj - 1;
+              while (next_fresh <= p_hi) {
+                mbar_wait(tempty_bar(next_fresh), (use_bits >> next_fresh) & 1u);
+                ++next_fresh;
+              }
+            }
+            const uint32_t dcol = tmem_base + p_lo * COUT;
             const uint32_t idesc = idesc1 + (uint32_t)(nj - 1) * kIdescNStep;
             mbar_wait(fbar, ph);
             tc_fence_after();
@@ -284,6 +264,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
               }
             }
             if (elect_one_sync()) umma_commit(fbar + 8u * kConvMaxStages);  // frees the activation stage when these MMAs retire
+            if (c == last_chunk) {
+              // output planes whose last contribution was just issued: q_rel - dil, and everything left after the last input plane
+              const int p_dn = (q_rel == q_end - 1) ? dteff - 1 : q_rel - dil;
+              while (next_done <= p_dn) {
+                if (elect_one_sync()) umma_commit(tfull_bar(next_done));
+                ++next_done;
+              }
+            }
             a_lo_st += stage16; fbar += 8u;
             if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; a_lo_st = a_lo_first; fbar = full_bar(0); }
           }
@@ -292,9 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             ++wcount;
           }
         }
-        if (elect_one_sync()) umma_commit(tfull_bar(acc));
-        acc ^= 1u;
-        if (acc == 0) accph ^= 1u;
+        use_bits ^= (dteff >= 32 ? 0xffffffffu : ((1u << dteff) - 1u));
       }
       __syncwarp();
     }
@@ -303,53 +289,68 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
     const int row = quarter * 32 + lane;
     const int hh = row >> 3, ww = row & 7;
-    uint32_t acc = 0, accph = 0;
+    uint32_t use_bits = 0;
     int run_n = -1;
     const float oscale = a.out_scale ? __ldg(a.out_scale) : 1.f;
+    const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16);
     auto flush_stats = [&]() {
       if (run_n < 0 || a.stats == nullptr) return;
 #pragma unroll
-      for (int cg = 0; cg < COUT / 16; ++cg) {
+      for (int cg = 0; cg < NCG; ++cg) {
         double* sp = a.stats + ((size_t)run_n * COUT + cg * 16 + (lane & 15)) * 2 + (lane >> 4);
-        atomicAdd(sp, (double)s_run[quarter][cg][lane]);
-        s_run[quarter][cg][lane] = 0.f;
+        atomicAdd(sp, s_run[quarter][cg][lane]);
+        s_run[quarter][cg][lane] = 0.0;
       }
     };
 #pragma unroll
-    for (int cg = 0; cg < COUT / 16; ++cg) s_run[quarter][cg][lane] = 0.f;
+    for (int cg = 0; cg < NCG; ++cg) s_run[quarter][cg][lane] = 0.0;
+    // hand every slot to the issuer zeroed (phase 0 of the "empty" barriers)
+#pragma unroll 1
+    for (int s = 0; s < 512 / 16; ++s) tmem_st16_zero(tacc + s * 16);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int s = 0; s < DT; ++s) mbar_arrive(tempty_bar(s));
+    const size_t plane_elems = (size_t)a.H * a.W * 8;
     for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<DT>(a, tile);
       if (t.n != run_n) { flush_stats(); run_n = t.n; }
       const int h = t.h0 + hh, w = t.w0 + ww;
       const bool inb = (h < a.H) && (w < a.W);
-      mbar_wait(tfull_bar(acc), accph);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kConvAccCols;
-      const size_t plane_elems = (size_t)a.H * a.W * 8;
-#pragma unroll 1
-      for (int cg = 0; cg < COUT / 16; ++cg) {
-        float red[32];
+      const int dteff = min(DT, t.Dp - t.d0);
+      // per-lane partial sums of this tile: red[cg*32 + i] = sum of channel cg*16+i, red[cg*32 + 16 + i] = sum of squares
+      float red[2 * COUT];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) red[i] = 0.f;
-        const size_t obase = ((size_t)(t.n * a.out_chunks_total + a.out_chunk_off + cg * 2) * a.D) * plane_elems +
-                             ((size_t)h * a.W + w) * 8;   // element offset
+      for (int i = 0; i < 2 * COUT; ++i) red[i] = 0.f;
 #pragma unroll 1
-        for (int s = 0; s < DT; ++s) {
-          const int dp = t.d0 + slot_plane<DT>(s, a.dil);
-          if (dp >= t.Dp) continue;  // warp-uniform
-          const int d = t.par + a.dstep * dp;
-          uint32_t v[16];
-          tmem_ld16(tacc + s * COUT + cg * 16, v);
-          tmem_ld_wait();
-          if (inb) {
+      for (int p = 0; p < dteff; ++p) {
+        const int d = t.par + a.dstep * (t.d0 + p);
+        mbar_wait(tfull_bar(p), (use_bits >> p) & 1u);
+        tc_fence_after();
+        uint32_t v[COUT];
+#pragma unroll
+        for (int cg = 0; cg < NCG; ++cg) tmem_ld16(tacc + p * COUT + cg * 16, v + cg * 16);
+        tmem_ld_wait();
+        // give the slot back (zeroed) before the slow part: conversions, global stores, statistics
+#pragma unroll
+        for (int cg = 0; cg < NCG; ++cg) tmem_st16_zero(tacc + p * COUT + cg * 16);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(p));
+        if (inb) {
+#pragma unroll
+          for (int cg = 0; cg < NCG; ++cg) {
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              f[i] = __uint_as_float(v[i]) * oscale;
-              red[i] += f[i];
-              red[16 + i] += f[i] * f[i];
+              f[i] = __uint_as_float(v[cg * 16 + i]) * oscale;
+              red[cg * 32 + i] += f[i];
+              red[cg * 32 + 16 + i] += f[i] * f[i];
             }
-            const size_t eo = obase + (size_t)d * plane_elems;
+            const size_t eo = ((size_t)(t.n * a.out_chunks_total + a.out_chunk_off + cg * 2) * a.D + d) * plane_elems +
+                              ((size_t)h * a.W + w) * 8;   // element offset
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               if (cg * 2 + k >= a.out_real_chunks) break;
@@ -376,17 +377,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             }
           }
         }
-        const float tot = warp_xreduce32(red, lane);
+      }
+      use_bits ^= (dteff >= 32 ? 0xffffffffu : ((1u << dteff) - 1u));
+      if (a.stats != nullptr) {
         // lane l < 16: sum of channel cg*16+l ; lane l >= 16: sum of squares of channel cg*16+l-16.
         // Totals are kept per warp across the tiles of this persistent CTA and flushed with one fp64 atomic
         // per (channel, moment) when the sample changes / at the end: same-address atomics serialise in L2.
-        s_run[quarter][cg][lane] += tot;
+#pragma unroll
+        for (int cg = 0; cg < NCG; ++cg) s_run[quarter][cg][lane] += (double)warp_xreduce32(red + cg * 32, lane);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      acc ^= 1u;
-      if (acc == 0) accph ^= 1u;
     }
     flush_stats();
   }
@@ -446,17 +445,17 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, uint16_t* __restri
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
-static constexpr uint32_t kSmemBudgetMax = 222u * 1024u;  // + 2 KB static smem (s_run) + alignment slack <= 227 KB
+static constexpr uint32_t kSmemBudgetMax = 220u * 1024u;  // + 4 KB static smem (s_run, fp64) + alignment slack <= 227 KB
 static uint32_t smem_budget() {   // SEUNET_CONV_SMEM_KB: experiment knob (leave room for co-resident streaming kernels)
   static const uint32_t v = [] {
     const char* e = getenv("SEUNET_CONV_SMEM_KB");
-    uint32_t kb = e ? (uint32_t)atoi(e) : 222u;
+    uint32_t kb = e ? (uint32_t)atoi(e) : 220u;
     return std::min(kSmemBudgetMax, std::max(64u, kb) * 1024u);
   }();
   return v;
 }
 #define kSmemBudget smem_budget()
-static constexpr uint32_t kBarBytes = 8u * (2 * kConvMaxStages + 32) + 128u;   // barriers + the 128-byte zero block
+static constexpr uint32_t kBarBytes = 8u * (2 * kConvMaxStages + 82) + 64u;   // stage / weight / per-slot accumulator barriers + TMEM address
 
 int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil, int bf16) {
   memset(g, 0, sizeof(*g));

@@ -9,7 +9,7 @@ constexpr int kConvMaxSteps = 40;   // UMMA K=16 steps per (input plane, channel
 constexpr int kConvTableSteps = 8;  // steps of the table-driven issue mode (Cin = 8 layers: 5)
 constexpr int kConvTileH = 16;      // one UMMA M=128 block = 16 (h) x 8 (w) voxels of one d-plane
 constexpr int kConvTileW = 8;
-constexpr int kConvAccCols = 256;   // TMEM columns per accumulator stage (2 stages = 512)
+constexpr int kConvAccCols = 512;   // TMEM columns of the (single) accumulator stage: DT = 512/COUT output-plane slots
 
 // Kernel arguments (passed by value as a __grid_constant__).
 struct ConvKArgs {

@@ -92,6 +92,23 @@ def test_largest_component_matches_oracle(shape, seed, thr):
         assert np.array_equal(got.astype(bool), want), (shape, fill)
 
 
+def test_largest_component_matches_reference_golden_vectors():
+    """tests/golden/postproc_max3d.npz hold outputs of the reference's OWN maximum_3d (util.py:58-75; oracle/make_golden.py):
+    area tie, probe-slice fallback, corner connectivity, hole filling, random blobs."""
+    z = np.load(os.path.join(GOLDEN, "postproc_max3d.npz"))
+    names = sorted(k[3:] for k in z.files if k.startswith("in."))
+    assert len(names) >= 7
+    for n in names:
+        vol = z["in." + n].astype(np.uint8)
+        pp = _pp(vol.shape)
+        got = pp.largest_component(torch.from_numpy(vol).cuda()).cpu().numpy()
+        assert np.array_equal(got, z["out." + n]), n
+        if n == "probe":
+            assert pp.last_info["used_second"]
+        if n == "tie":
+            assert pp.last_info["largest"] == pp.last_info["second"] == 12 and not pp.last_info["used_second"]
+
+
 def test_largest_component_diagonal_connectivity_and_holes():
     m = np.zeros((10, 10, 40), np.uint8)
     for t in range(8):                      # a 26-connected diagonal staircase: one component
