@@ -51,54 +51,132 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKArgs& a, int tile) {
   return t;
 }
 
-// The 9 in-plane taps x J 16-channel blocks of one input plane, fully unrolled (J = 0: runtime block count).  Runs on
-// the whole issuer warp with uniform operands; only the tcgen05.mma itself is issued by the elected lane.
-template <int J>
-__device__ __forceinline__ void issue_taps3(uint32_t dcol, uint32_t a_lo_st, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                            uint32_t idesc, uint32_t kh_step, uint32_t kw_step, uint32_t j_step,
-                                            uint32_t b_step, int jsteps) {
-  // Only a few tcgen05.mma per basic block: every in-flight instruction pins its own uniform-register operands, and a
-  // fully unrolled plane (36 of them) pushes the loop-carried state out of the uniform register file.
-  uint32_t a_row = a_lo_st;
-#pragma unroll 1
-  for (int kh = 0; kh < 3; ++kh) {
-    uint32_t a_tap = a_row;
-#pragma unroll 1
-    for (int kw = 0; kw < 3; ++kw) {
-      uint32_t a_lo = a_tap;
-      if (J > 0) {
+// One input plane of a 3x3x3 layer: 9 in-plane taps x J 16-channel blocks, fully unrolled.  Tap offsets into the halo tile
+// and weight-image offsets are IMMEDIATES (functions of DIL, J, COUT only); the only register operands are the plane's
+// base descriptors.  Called by the single issuing thread.
+template <int COUT, int DIL, int J>
+__device__ __forceinline__ void issue_plane3(uint32_t dcol, uint32_t a_plane, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t j_step) {
+  constexpr uint32_t LW = kConvTileW + 2 * DIL;     // halo line in voxels (= 16-byte units)
+  constexpr uint32_t BST = 2u * 3u * COUT;          // one K=16 step of the weight image: 2 K halves x 3 kd blocks x COUT rows
+  uint32_t aj[J];
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-          if (elect_one_sync()) umma_f16_lohi(dcol, a_lo, a_hi, b_lo, b_hi, idesc);
-          a_lo += j_step; b_lo += b_step;
-        }
-      } else {
+  for (int j = 0; j < J; ++j) aj[j] = a_plane + (uint32_t)j * j_step;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+        umma_f16_lohi(dcol, aj[j] + (uint32_t)(kh * DIL * LW + kw * DIL), a_hi, b_lo + (uint32_t)(((kh * 3 + kw) * J + j) * BST), b_hi, idesc);
+}
+
+// Accumulator organisation (round 2).  The whole TMEM (512 columns) is ONE stage of DT = 512/COUT output-plane slots in
+// kConvGroups groups with a full/empty mbarrier pair each:
+//   * the issuer acquires a group (waits for "empty": drained by the epilogue) right before the first input plane that
+//     touches it, clears it with one zero-operand UMMA, accumulates unconditionally, and commits "full" right after the
+//     last input plane that touches it (last channel chunk);
+//   * the epilogue drains the groups in order as they complete: tcgen05.ld, conversions / global stores / statistics,
+//     arrive "empty".
+// The next tile starts on group 0 while the last group of the previous tile is still being drained, so the epilogue is
+// hidden as with two half-size stages, but a tile is twice as deep: (DT + 2)/DT input planes per output plane instead of
+// (DT/2 + 2)/(DT/2) - 1.25 instead of 1.5 for COUT = 64, 1.125 instead of 1.25 for COUT = 32.
+// Every tile runs the SAME schedule: DT + 2 input planes (TMA zero-fills planes outside the volume, their MMAs are
+// skipped) in boxes of `pb` planes, so the issuer pays one mbarrier wait and one commit per BOX, not per plane -
+// measured (tools/umma_bench.cu, groups sync/issue): a try_wait on a completed barrier costs the issuing thread ~120
+// cycles and a tcgen05.commit ~125, neither overlaps with issuing, and an M=128 tcgen05.mma cannot be issued faster than
+// one per ~45 cycles whatever N is, so for N <= 96 every cycle of issuer overhead is a cycle of idle tensor pipe.
+// Issue modes of the per-tile plane loop (one template instance each, selected ONCE per tile and channel chunk: inside the
+// loop there is no layer-dependent branching and no kernel-parameter reload - ncu's source view showed the issuer stalled
+// on the latency of exactly those uniform-datapath compare/branch chains, ~500 cycles per plane).
+enum { kModeTaps3 = 0 /* + (dil-1)*3 + log2(J): six 3x3x3 variants */, kModePaired = 6, kModePointwise = 7 };
+
+template <int COUT, int MODE>
+__device__ __forceinline__ void issue_mode(uint32_t dcol, uint32_t a_plane, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t j_step, uint32_t b_step, int jsteps, const uint2* dlt) {
+  if (MODE < 6) {
+    issue_plane3<COUT, 1 + MODE / 3, 1 << (MODE % 3)>(dcol, a_plane, a_hi, b_lo, b_hi, idesc, j_step);
+  } else if (MODE == kModePaired) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) umma_f16_lohi(dcol, a_plane + dlt[s].x, a_hi, b_lo + dlt[s].y, b_hi, idesc);   // paired taps (Cin = 8)
+  } else {
 #pragma unroll 1
-        for (int j = 0; j < jsteps; ++j) {
-          if (elect_one_sync()) umma_f16_lohi(dcol, a_lo, a_hi, b_lo, b_hi, idesc);
-          a_lo += j_step; b_lo += b_step;
-        }
-      }
-      a_tap += kw_step;
+    for (int j = 0; j < jsteps; ++j) {
+      umma_f16_lohi(dcol, a_plane, a_hi, b_lo, b_hi, idesc);
+      a_plane += j_step; b_lo += b_step;
     }
-    a_row += kh_step;
   }
 }
 
-// Accumulator organisation (round 2).  The whole TMEM (512 columns) is ONE stage of DT = 512/COUT output-plane slots, and
-// every slot has its own full/empty mbarrier pair:
-//   * the issuer acquires slot p (waits for "empty": drained AND zeroed by the epilogue) right before the first input
-//     plane that touches output plane p, accumulates unconditionally, and commits "full" for p right after the last input
-//     plane that touches it (input p + dil, last channel chunk);
-//   * the epilogue drains the slots in plane order as they complete: tcgen05.ld, then tcgen05.st of zeros (off the tensor
-//     pipe), arrive "empty", and only then the conversions / global stores / statistics.
-// The next tile starts on slot 0 while the last slots of the previous tile are still being drained, so the epilogue is
-// hidden exactly as with two half-size stages, but a tile is twice as deep: (DT + 2)/DT input planes per output plane
-// instead of (DT/2 + 2)/(DT/2) - 1.25 instead of 1.5 for COUT = 64, 1.125 instead of 1.25 for COUT = 32.
+// Loop-carried state of the issuer across boxes / tiles (activation ring position).
+struct IssueRing { uint32_t st, ph, a_lo_st, fbar; };
+
+// All planes k = 0 .. KMAX of one (tile, channel chunk).  Plane k first touches output plane k (3x3x3: through its kd = 0
+// tap) and gives output plane k - 2*DIL its last contribution, so the accumulator-group events sit at fixed k:
+//   wait "empty" + clear of group k/G          when k % G == 0, k < DT              (first channel chunk only)
+//   commit "full" of group (k - 2*DIL)/G       when (k - 2*DIL) % G == G - 1        (last channel chunk only)
+template <int COUT, int MODE>
+__device__ __forceinline__ void issue_tile(IssueRing& r, const uint32_t a_lo_first, const uint32_t full0, const int nstages,
+                                           const uint32_t stage16, const uint32_t plane16, const int pb, const int kv0, const int kv1,
+                                           const bool first_chunk, const bool last_chunk, const uint32_t tphase, const uint32_t tmem_base,
+                                           const uint32_t tempty0, const uint32_t tfull0, const uint32_t idesc1, const uint32_t idesc_clear,
+                                           const uint64_t zdesc, const uint32_t a_hi, const uint32_t b_hi, const uint32_t b_lo_slot,
+                                           const uint32_t j_step, const uint32_t b_step, const int jsteps, const uint2* dlt) {
+  constexpr int DT = kConvAccCols / COUT;
+  constexpr int G = DT / kConvGroups;
+  constexpr int DIL = (MODE == kModePointwise) ? 0 : 1;     // plane distance of the kd taps (parity classes make it 1)
+  constexpr int KMAX = DT - 1 + 2 * DIL;
+  constexpr uint32_t kIdescNStep = (uint32_t)(COUT >> 3) << 17;   // one more kd block along N
+  uint32_t dcol = tmem_base, idesc = idesc1, b_lo = b_lo_slot + (uint32_t)(2 * DIL * COUT);
+  uint32_t a_plane = r.a_lo_st;
+  int box_left = 0;
+#pragma unroll 1
+  for (int k = 0; k <= KMAX; ++k) {
+    if (box_left == 0) {
+      mbar_wait(r.fbar, r.ph);      // TMA -> mbarrier -> MMA: ordered by the mbarrier itself
+      a_plane = r.a_lo_st;
+      box_left = pb;
+    }
+    if (first_chunk && k < DT && (k % G) == 0) {
+      mbar_wait(tempty0 + 8u * (uint32_t)(k / G), tphase);
+      tc_fence_after();
+      umma_f16(tmem_base + k * COUT, zdesc, zdesc, idesc_clear, 0u);
+    }
+    if (k >= kv0 && k <= kv1)       // planes outside the volume arrive as zeros: nothing to add
+      issue_mode<COUT, MODE>(dcol, a_plane, a_hi, b_lo, b_hi, idesc, j_step, b_step, jsteps, dlt);
+    if (last_chunk && k >= 2 * DIL && ((k - 2 * DIL) % G) == G - 1) umma_commit(tfull0 + 8u * (uint32_t)((k - 2 * DIL) / G));
+    // next plane: stacked kd blocks grow 1 -> 2 -> 3 at the start of the tile, shrink 3 -> 2 -> 1 at its end
+    a_plane += plane16;
+    if (DIL == 1) {
+      if (k < 2) { idesc += kIdescNStep; b_lo -= COUT; }
+      else { dcol += COUT; if (k >= DT - 1) idesc -= kIdescNStep; }
+    } else {
+      dcol += COUT;
+    }
+    if (--box_left == 0 || k == KMAX) {
+      umma_commit(r.fbar + 8u * kConvMaxStages);  // frees the activation stage when these MMAs retire
+      box_left = 0;
+      r.a_lo_st += stage16; r.fbar += 8u;
+      if (++r.st == (uint32_t)nstages) { r.st = 0; r.ph ^= 1u; r.a_lo_st = a_lo_first; r.fbar = full0; }
+    }
+  }
+}
+
+#ifdef SEUNET_CONV_PROFILE
+// developer build (tools/conv_profile.sh): per-CTA cycle counters of the three roles, printed by the host after each launch
+__device__ long long g_conv_prof[148 * 8];
+#define PROF_T0(v) const long long v = clock64()
+#define PROF_ADD(acc, v) acc += clock64() - v
+#else
+#define PROF_T0(v)
+#define PROF_ADD(acc, v)
+#endif
+
 template <int COUT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvKArgs a) {
   constexpr int DT = kConvAccCols / COUT;
+  constexpr int G = DT / kConvGroups;   // output planes per accumulator group
   constexpr int NCG = COUT / 16;
   // per-epilogue-warp running InstanceNorm partial sums.  fp64: the per-tile fp32 partials are a fixed function of the
   // tile, so the statistics do not depend on which tiles a CTA happens to process (batch size, grid) beyond fp64 rounding.
@@ -116,8 +194,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   auto wfull_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + i); };
   auto wempty_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 8 + i); };
   auto tfull_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 16 + i); };
-  auto tempty_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 48 + i); };
-  const uint32_t tmem_slot_addr = bar_addr + 8u * (2 * kConvMaxStages + 80);
+  auto tempty_bar = [&](int i) { return bar_addr + 8u * (2 * kConvMaxStages + 24 + i); };
+  const uint32_t tmem_slot_addr = bar_addr + 8u * (2 * kConvMaxStages + 32);
+  const uint32_t zero_addr = bar_addr + 8u * (2 * kConvMaxStages + 48);   // 128 zero bytes (128-byte aligned): operands of the accumulator-clearing UMMA
 
   // warp index through a shuffle so that the compiler KNOWS it is warp-uniform: the role branches and everything
   // inside them (loop counters, descriptors) can then live in uniform registers, which UTCHMMA needs anyway.
@@ -127,10 +206,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   if (threadIdx.x == 0) {
     for (int i = 0; i < a.nstages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
     for (int i = 0; i < a.wslots; ++i) { mbar_init(wfull_bar(i), 1); mbar_init(wempty_bar(i), 1); }
-    for (int i = 0; i < DT; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
+    for (int i = 0; i < kConvGroups; ++i) { mbar_init(tfull_bar(i), 1); mbar_init(tempty_bar(i), 4); }
     fence_mbar_init();
     tma_prefetch_desc(&tmap);
   }
+  if (threadIdx.x < 32) asm volatile("st.shared.u32 [%0], %1;" ::"r"(zero_addr + 4u * threadIdx.x), "r"(0u) : "memory");
+  fence_proxy_async();   // generic-proxy zeros must be visible to the tensor core (async proxy)
   if (warp == 1) {
     tmem_alloc(tmem_slot_addr, 512);
     tmem_relinquish();
@@ -143,11 +224,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
 
   const bool resident = a.nchunks <= a.wslots;
+  const int q0 = -a.dil;                 // first input plane of a tile (tile-relative); dil is 1 (3x3x3) or 0 (1x1x1) here
 
   if (warp == 0) {
     // =================================== TMA producer ===================================
     if (lane == 0) {
       uint32_t st = 0, ph = 0, wcount = 0;
+#ifdef SEUNET_CONV_PROFILE
+      long long p_wait = 0; PROF_T0(p_t0);
+#endif
       auto load_weights = [&](int chunk, int slot) {
         mbar_expect_tx(wfull_bar(slot), a.wchunk_bytes);
         const uint8_t* src = a.wimg + (size_t)chunk * a.wchunk_bytes;
@@ -161,8 +246,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         for (int c = 0; c < a.nchunks; ++c) load_weights(c, c);
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<DT>(a, tile);
-        const int dteff = min(DT, t.Dp - t.d0);
-        const int q_begin = max(-a.dil, -t.d0), q_end = min(dteff + a.dil, t.Dp - t.d0);   // same range as the issuer
         for (int c = 0; c < a.nchunks; ++c) {
           if (!resident) {
             const int slot = wcount % a.wslots;
@@ -171,127 +254,102 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             load_weights(c, slot);
             ++wcount;
           }
-          for (int q_rel = q_begin; q_rel < q_end; ++q_rel) {
-            mbar_wait(empty_bar(st), ph ^ 1u);
+          for (int bx = 0; bx < a.nboxes; ++bx) {
+            // one box = pb consecutive planes of the tile's parity class; planes outside the volume arrive as zeros
+            { PROF_T0(tw); mbar_wait(empty_bar(st), ph ^ 1u); PROF_ADD(p_wait, tw); }
             mbar_expect_tx(full_bar(st), a.box_bytes);
             tma_load_4d(s_addr + st * a.stage_bytes, &tmap, full_bar(st),
-                        8 * (t.w0 - a.halo), t.h0 - a.halo, t.par + a.dstep * (t.d0 + q_rel),
+                        8 * (t.w0 - a.halo), t.h0 - a.halo, t.par + a.dstep * (t.d0 + q0 + bx * a.pb),
                         t.n * a.in_chunks_total + a.in_chunk_off + c * a.kc8);
             if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
           }
         }
       }
+#ifdef SEUNET_CONV_PROFILE
+      if (blockIdx.x < 148) { g_conv_prof[blockIdx.x * 8 + 0] = clock64() - p_t0; g_conv_prof[blockIdx.x * 8 + 1] = p_wait; }
+#endif
     }
   } else if (warp == 1) {
     // =================================== UMMA issuer ===================================
-    // The whole warp runs this loop with warp-uniform control flow so that descriptors live in
-    // uniform registers; only the tcgen05.mma / tcgen05.commit themselves are issued by one elected lane.
-    {
-      uint32_t st = 0, ph = 0, wcount = 0, wready = 0;
-      uint32_t use_bits = 0;                  // bit p: parity of the number of completed uses of accumulator slot p
+    // ONE thread runs the whole issue loop.  (Round 1 ran it warp-converged with an elected lane per instruction; ncu's
+    // source view shows what that costs: the BSYNC that re-converges the warp after every `if (elect_one_sync())` region
+    // waits on the scoreboard of the tcgen05.mma instructions inside it, i.e. drains the tensor pipe's instruction queue -
+    // once per MMA in round 1 (66-68 cycles per MMA instead of 56), once per plane with an unrolled plane.  A single
+    // active thread never re-converges, so the queue stays full across planes, boxes and tiles.)
+    // (`elect_one_sync()` rather than `lane == 0`: ptxas recognises the elect pattern as "exactly one thread active" and keeps
+    // the descriptor arithmetic on the uniform datapath; with a lane test every tcgen05.mma is wrapped in a vote loop.)
+    if (elect_one_sync()) {
+      uint32_t wcount = 0, wready = 0, tphase = 0;
       const uint32_t idesc1 = umma_idesc(a.fmt, 128, COUT);
-      constexpr uint32_t kIdescNStep = (uint32_t)(COUT >> 3) << 17;   // one more kd block along N
-      const int dil = a.dil, nkd = a.nkd;
-      const uint32_t a_hi = a.a_hi, b_hi = a.b_hi, stage16 = a.stage16;
+      // One UMMA with all-zero operands and accumulate OFF clears a whole accumulator group (G * COUT = 128 columns, 64
+      // cycles) right after it is acquired: 4x cheaper than tcgen05.st from the epilogue warps, whose TMEM traffic stalls
+      // the tensor pipe just like their tcgen05.ld does (measured: ~30 cycles of lost MMA time per x16 access).
+      const uint32_t idesc_clear = umma_idesc(a.fmt, 128, G * COUT);
+      const uint64_t zdesc = umma_desc(zero_addr, 0, 0);   // every core matrix reads the same 128 zero bytes
+      const int pb = a.pb;
+      const uint32_t a_hi = a.a_hi, b_hi = a.b_hi, stage16 = a.stage16, plane16 = a.plane16;
       const uint32_t a_lo_first = a.a_lo0 | ((s_addr & 0x3FFFFu) >> 4);
       const uint32_t b_lo_lbo = ((a.b_lbo >> 4) & 0x3FFFu) << 16;
-      uint32_t a_lo_st = a_lo_first;          // A descriptor low word of ring stage st
-      uint32_t fbar = full_bar(0);            // full barrier of ring stage st (empty barrier = + 8 * kConvMaxStages)
-      const int regular = a.regular, ntap = a.ntap, jsteps = a.jsteps;
-      // bit mask instead of the count, so that the dispatch below compiles to uniform branches and not to a jump table
-      const int jmode = jsteps == 1 ? 1 : (jsteps == 2 ? 2 : (jsteps == 4 ? 4 : 8));
-      const uint32_t kh_step = a.kh_step, kw_step = a.kw_step, j_step = a.j_step, b_step = a.b_step;
+      // activation ring position: stage, phase, A descriptor low word and full barrier of the stage (empty barrier = + 8 * kConvMaxStages)
+      IssueRing ring{0u, 0u, a_lo_first, full_bar(0)};
+      const int jsteps = a.jsteps;
+      const int mode = !a.regular ? kModePaired : (a.ntap == 3 ? (a.cdil - 1) * 3 + (jsteps == 1 ? 0 : (jsteps == 2 ? 1 : 2)) : kModePointwise);
+      const uint32_t j_step = a.j_step, b_step = a.b_step;
       const int last_chunk = a.nchunks - 1;
+#ifdef SEUNET_CONV_PROFILE
+      long long i_full = 0, i_tempty = 0, i_w = 0; PROF_T0(i_t0);
+#endif
       for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
         const TileCoord t = decode_tile<DT>(a, tile);
         const int D = t.Dp;
-        const int dteff = min(DT, D - t.d0);
-        // input planes q_rel in [-dil, dteff + dil) that exist in the volume
-        const int q_begin = max(-dil, -t.d0), q_end = min(dteff + dil, D - t.d0);
-        int next_fresh = 0, next_done = 0;    // output planes not yet acquired / not yet committed
         for (int c = 0; c < a.nchunks; ++c) {
           int slot;
           if (resident) {
             slot = c;
-            if (!((wready >> c) & 1u)) { mbar_wait(wfull_bar(c), 0); wready |= 1u << c; }
+            if (!((wready >> c) & 1u)) { PROF_T0(tw); mbar_wait(wfull_bar(c), 0); wready |= 1u << c; PROF_ADD(i_w, tw); }
           } else {
             slot = wcount % a.wslots;
-            mbar_wait(wfull_bar(slot), (wcount / a.wslots) & 1u);
+            PROF_T0(tw); mbar_wait(wfull_bar(slot), (wcount / a.wslots) & 1u); PROF_ADD(i_w, tw);
           }
           const uint32_t b_lo_slot = b_lo_lbo | (((w_addr + slot * a.wchunk_bytes) & 0x3FFFFu) >> 4);
-          for (int q_rel = q_begin; q_rel < q_end; ++q_rel) {
-            // kd block j (j = 0,1,2) of this input plane feeds output plane q_rel + (j-1)*dil; the valid ones are contiguous
-            int jlo = 0, nj = 1, p_lo = q_rel;
-            if (nkd == 3) {
-              const int p0 = q_rel - dil, p2 = q_rel + dil;
-              jlo = (p0 < 0) + (q_rel < 0);                                   // p2 >= 0 always holds here
-              nj = (p0 < dteff) + (q_rel < dteff) + (p2 < dteff) - jlo;
-              p_lo = q_rel + (jlo - 1) * dil;
-            }
-            if (c == 0) {
-              // first touch of output planes <= p_hi: their slots must have been drained and zeroed by the epilogue
-              const int p_hi = p_lo + nj - 1;
-              while (next_fresh <= p_hi) {
-                mbar_wait(tempty_bar(next_fresh), (use_bits >> next_fresh) & 1u);
-                ++next_fresh;
-              }
-            }
-            const uint32_t dcol = tmem_base + p_lo * COUT;
-            const uint32_t idesc = idesc1 + (uint32_t)(nj - 1) * kIdescNStep;
-            mbar_wait(fbar, ph);
-            tc_fence_after();
-            uint32_t b_lo = b_lo_slot + (uint32_t)(jlo * COUT);
-            if (regular) {
-              if (ntap == 3) {
-                // (an if-chain, not a switch: a jump table would leave the uniform datapath)
-                if (jmode == 1) issue_taps3<1>(dcol, a_lo_st, a_hi, b_lo, b_hi, idesc, kh_step, kw_step, j_step, b_step, 1);
-                else if (jmode & 2) issue_taps3<2>(dcol, a_lo_st, a_hi, b_lo, b_hi, idesc, kh_step, kw_step, j_step, b_step, 2);
-                else if (jmode & 4) issue_taps3<4>(dcol, a_lo_st, a_hi, b_lo, b_hi, idesc, kh_step, kw_step, j_step, b_step, 4);
-                else issue_taps3<0>(dcol, a_lo_st, a_hi, b_lo, b_hi, idesc, kh_step, kw_step, j_step, b_step, jsteps);
-              } else {
-                uint32_t a_lo = a_lo_st;
-#pragma unroll 1
-                for (int j = 0; j < jsteps; ++j) {
-                  if (elect_one_sync()) umma_f16_lohi(dcol, a_lo, a_hi, b_lo, b_hi, idesc);
-                  a_lo += j_step; b_lo += b_step;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int s = 0; s < 5; ++s) {   // paired taps (Cin = 8): always 5 steps
-                const uint2 dl = a.dlt[s];
-                if (elect_one_sync()) umma_f16_lohi(dcol, a_lo_st + dl.x, a_hi, b_lo + dl.y, b_hi, idesc);
-              }
-            }
-            if (elect_one_sync()) umma_commit(fbar + 8u * kConvMaxStages);  // frees the activation stage when these MMAs retire
-            if (c == last_chunk) {
-              // output planes whose last contribution was just issued: q_rel - dil, and everything left after the last input plane
-              const int p_dn = (q_rel == q_end - 1) ? dteff - 1 : q_rel - dil;
-              while (next_done <= p_dn) {
-                if (elect_one_sync()) umma_commit(tfull_bar(next_done));
-                ++next_done;
-              }
-            }
-            a_lo_st += stage16; fbar += 8u;
-            if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; a_lo_st = a_lo_first; fbar = full_bar(0); }
-          }
+          const int kv0 = max(0, -q0 - t.d0), kv1 = D - 1 - t.d0 - q0;   // planes inside the volume (k = q - q0)
+#define SEUNET_ISSUE_TILE(M) issue_tile<COUT, M>(ring, a_lo_first, full_bar(0), a.nstages, stage16, plane16, pb, kv0, kv1, c == 0, \
+                                                 c == last_chunk, tphase, tmem_base, tempty_bar(0), tfull_bar(0), idesc1, idesc_clear, \
+                                                 zdesc, a_hi, b_hi, b_lo_slot, j_step, b_step, jsteps, a.dlt)
+          // (an if-chain, not a switch: a jump table would leave the uniform datapath)
+          if (mode == 0) SEUNET_ISSUE_TILE(0);
+          else if (mode == 1) SEUNET_ISSUE_TILE(1);
+          else if (mode == 2) SEUNET_ISSUE_TILE(2);
+          else if (mode == 3) SEUNET_ISSUE_TILE(3);
+          else if (mode == 4) SEUNET_ISSUE_TILE(4);
+          else if (mode == 5) SEUNET_ISSUE_TILE(5);
+          else if (mode == kModePaired) SEUNET_ISSUE_TILE(kModePaired);
+          else SEUNET_ISSUE_TILE(kModePointwise);
+#undef SEUNET_ISSUE_TILE
           if (!resident) {
-            if (elect_one_sync()) umma_commit(wempty_bar(slot));
+            umma_commit(wempty_bar(slot));
             ++wcount;
           }
         }
-        use_bits ^= (dteff >= 32 ? 0xffffffffu : ((1u << dteff) - 1u));
+        tphase ^= 1u;
       }
-      __syncwarp();
+#ifdef SEUNET_CONV_PROFILE
+      if (blockIdx.x < 148) {
+        g_conv_prof[blockIdx.x * 8 + 2] = clock64() - i_t0; g_conv_prof[blockIdx.x * 8 + 3] = i_full;
+        g_conv_prof[blockIdx.x * 8 + 4] = i_tempty; g_conv_prof[blockIdx.x * 8 + 5] = i_w;
+      }
+#endif
     }
+    __syncwarp();
   } else {
     // =================================== epilogue (4 warps) ===================================
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) are the ones this warp may read
     const int row = quarter * 32 + lane;
     const int hh = row >> 3, ww = row & 7;
-    uint32_t use_bits = 0;
+    uint32_t tphase = 0;
     int run_n = -1;
-    const float oscale = a.out_scale ? __ldg(a.out_scale) : 1.f;
+    const bool has_scale = a.out_scale != nullptr;
+    const float oscale = has_scale ? __ldg(a.out_scale) : 1.f;
     const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16);
     auto flush_stats = [&]() {
       if (run_n < 0 || a.stats == nullptr) return;
@@ -304,15 +362,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     };
 #pragma unroll
     for (int cg = 0; cg < NCG; ++cg) s_run[quarter][cg][lane] = 0.0;
-    // hand every slot to the issuer zeroed (phase 0 of the "empty" barriers)
-#pragma unroll 1
-    for (int s = 0; s < 512 / 16; ++s) tmem_st16_zero(tacc + s * 16);
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
+    // all groups start out free (phase 0 of the "empty" barriers); the issuer clears a group when it acquires it
     if (lane == 0)
-      for (int s = 0; s < DT; ++s) mbar_arrive(tempty_bar(s));
+      for (int s = 0; s < kConvGroups; ++s) mbar_arrive(tempty_bar(s));
     const size_t plane_elems = (size_t)a.H * a.W * 8;
+#ifdef SEUNET_CONV_PROFILE
+    long long e_wait = 0; PROF_T0(e_t0);
+#endif
     for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
       const TileCoord t = decode_tile<DT>(a, tile);
       if (t.n != run_n) { flush_stats(); run_n = t.n; }
@@ -324,61 +380,72 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
       for (int i = 0; i < 2 * COUT; ++i) red[i] = 0.f;
 #pragma unroll 1
-      for (int p = 0; p < dteff; ++p) {
-        const int d = t.par + a.dstep * (t.d0 + p);
-        mbar_wait(tfull_bar(p), (use_bits >> p) & 1u);
+      for (int g = 0; g < kConvGroups; ++g) {
+        { PROF_T0(tw); mbar_wait(tfull_bar(g), tphase); PROF_ADD(e_wait, tw); }
         tc_fence_after();
-        uint32_t v[COUT];
+#pragma unroll 1
+        for (int p = g * G; p < (g + 1) * G; ++p) {
+          if (p < dteff) {   // (warp-uniform) planes past the end of the volume hold nothing
+            const int d = t.par + a.dstep * (t.d0 + p);
+            uint32_t v[COUT];
+#ifdef SEUNET_CONV_PROFILE
+            if (a.dbg & 1) {   // experiment: no TMEM reads at all (results are garbage)
 #pragma unroll
-        for (int cg = 0; cg < NCG; ++cg) tmem_ld16(tacc + p * COUT + cg * 16, v + cg * 16);
-        tmem_ld_wait();
-        // give the slot back (zeroed) before the slow part: conversions, global stores, statistics
-#pragma unroll
-        for (int cg = 0; cg < NCG; ++cg) tmem_st16_zero(tacc + p * COUT + cg * 16);
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(p));
-        if (inb) {
-#pragma unroll
-          for (int cg = 0; cg < NCG; ++cg) {
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              f[i] = __uint_as_float(v[cg * 16 + i]) * oscale;
-              red[cg * 32 + i] += f[i];
-              red[cg * 32 + 16 + i] += f[i] * f[i];
-            }
-            const size_t eo = ((size_t)(t.n * a.out_chunks_total + a.out_chunk_off + cg * 2) * a.D + d) * plane_elems +
-                              ((size_t)h * a.W + w) * 8;   // element offset
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              if (cg * 2 + k >= a.out_real_chunks) break;
-              const size_t ek = eo + (size_t)k * a.D * plane_elems;
-              if (a.out_bf16) {   // gradient-format output (grad_t), optionally accumulating
-                grad_t* ok = reinterpret_cast<grad_t*>(a.out) + ek;
-#ifdef SEUNET_HAVE_RED_GRAD8
-                // gradient accumulation of fan-out nodes: vector reduction in L2 instead of load + add + store (the read
-                // latency, once per plane and chunk, made the epilogue the bottleneck of the accumulating dgrads)
-                if (a.accum_out) red_grad8(ok, f + 8 * k);
-                else st_grad8(ok, f + 8 * k);
-#else
-                if (a.accum_out) {
-                  float old[8];
-                  ld_grad8_cached(ok, old);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) f[8 * k + i] += old[i];
-                }
-                st_grad8(ok, f + 8 * k);
+              for (int i = 0; i < COUT; ++i) v[i] = 0x3f800000u;
+            } else
 #endif
-              } else {
-                st_chunk(reinterpret_cast<uint16_t*>(a.out) + ek, floats_to_chunk(f + 8 * k));
+            {
+#pragma unroll
+              for (int cg = 0; cg < NCG; ++cg) tmem_ld16(tacc + p * COUT + cg * 16, v + cg * 16);
+              tmem_ld_wait();
+            }
+            if (inb) {
+#pragma unroll
+              for (int cg = 0; cg < NCG; ++cg) {
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  f[i] = __uint_as_float(v[cg * 16 + i]);
+                  if (has_scale) f[i] *= oscale;
+                  red[cg * 32 + i] += f[i];
+                  red[cg * 32 + 16 + i] += f[i] * f[i];
+                }
+                const size_t eo = ((size_t)(t.n * a.out_chunks_total + a.out_chunk_off + cg * 2) * a.D + d) * plane_elems +
+                                  ((size_t)h * a.W + w) * 8;   // element offset
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                  if (cg * 2 + k >= a.out_real_chunks) break;
+                  const size_t ek = eo + (size_t)k * a.D * plane_elems;
+                  if (a.out_bf16) {   // gradient-format output (grad_t), optionally accumulating
+                    grad_t* ok = reinterpret_cast<grad_t*>(a.out) + ek;
+#ifdef SEUNET_HAVE_RED_GRAD8
+                    // gradient accumulation of fan-out nodes: vector reduction in L2 instead of load + add + store (the read
+                    // latency, once per plane and chunk, made the epilogue the bottleneck of the accumulating dgrads)
+                    if (a.accum_out) red_grad8(ok, f + 8 * k);
+                    else st_grad8(ok, f + 8 * k);
+#else
+                    if (a.accum_out) {
+                      float old[8];
+                      ld_grad8_cached(ok, old);
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) f[8 * k + i] += old[i];
+                    }
+                    st_grad8(ok, f + 8 * k);
+#endif
+                  } else {
+                    st_chunk(reinterpret_cast<uint16_t*>(a.out) + ek, floats_to_chunk(f + 8 * k));
+                  }
+                }
               }
             }
           }
         }
+        // give the group back (the issuer clears it with one UMMA when it re-acquires it)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(g));
       }
-      use_bits ^= (dteff >= 32 ? 0xffffffffu : ((1u << dteff) - 1u));
+      tphase ^= 1u;
       if (a.stats != nullptr) {
         // lane l < 16: sum of channel cg*16+l ; lane l >= 16: sum of squares of channel cg*16+l-16.
         // Totals are kept per warp across the tiles of this persistent CTA and flushed with one fp64 atomic
@@ -388,6 +455,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       }
     }
     flush_stats();
+#ifdef SEUNET_CONV_PROFILE
+    if (warp == 2 && lane == 0 && blockIdx.x < 148) { g_conv_prof[blockIdx.x * 8 + 6] = clock64() - e_t0; g_conv_prof[blockIdx.x * 8 + 7] = e_wait; }
+#endif
   }
 
   tc_fence_before();
@@ -455,7 +525,7 @@ static uint32_t smem_budget() {   // SEUNET_CONV_SMEM_KB: experiment knob (leave
   return v;
 }
 #define kSmemBudget smem_budget()
-static constexpr uint32_t kBarBytes = 8u * (2 * kConvMaxStages + 82) + 64u;   // stage / weight / per-slot accumulator barriers + TMEM address
+static constexpr uint32_t kBarBytes = 8u * (2 * kConvMaxStages + 48) + 128u + 64u;   // stage / weight / accumulator-group barriers, TMEM address, zero block
 
 int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil, int bf16) {
   memset(g, 0, sizeof(*g));
@@ -510,12 +580,27 @@ int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil,
   if (g->paired) g->wslots = 1;
   if (g->nsteps > kConvMaxSteps) { seunet_set_error("conv: too many steps"); return 1; }
   g->wchunk_bytes = (uint32_t)g->nsteps * 2u * nkd * g->COUT * 16u;
-  g->box_bytes = (uint32_t)HV * g->KC * 2u;
-  g->stage_bytes = (g->box_bytes + 127u) & ~127u;
   const uint32_t wregion = ((uint32_t)g->wslots * g->wchunk_bytes + 127u) & ~127u;
-  int nst = (int)((kSmemBudget - wregion - kBarBytes - 128u) / g->stage_bytes);
-  // TMA is latency-bound: keep >= ~96 KB in flight per SM when the stages are small (ec1/ec2: 2.9 KB per plane)
-  nst = std::min(nst, std::max(4, std::min(kConvMaxStages, (int)(98304u / g->stage_bytes))));
+  const uint32_t avail = kSmemBudget - wregion - kBarBytes - 128u;
+  // Planes per TMA box / ring stage.  A tile always consumes DTIN = DT (+2 for 3x3x3) input planes; the issuer pays ~300
+  // cycles of synchronisation per box (see the kernel comment), an unused plane at the end of the last box only costs
+  // L2->SMEM traffic.  At least two stages must fit.
+  const uint32_t plane_bytes = (uint32_t)HV * g->KC * 2u;
+  const int DTIN = kConvAccCols / g->COUT + (nkd == 3 ? 2 : 0);
+  const uint32_t cap = std::min<uint32_t>(56u * 1024u, avail / 2u);
+  int best_pb = 1; long best_cost = -1;
+  for (int pb = 1; pb <= std::min(DTIN, 17); ++pb) {
+    if (pb > 1 && (uint32_t)pb * plane_bytes > cap) break;
+    const int nb = (DTIN + pb - 1) / pb;
+    const long cost = (long)nb * 300 + (long)(nb * pb - DTIN) * 40;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_pb = pb; }
+  }
+  g->pb = best_pb; g->nboxes = (DTIN + best_pb - 1) / best_pb;
+  g->box_bytes = (uint32_t)best_pb * plane_bytes;
+  g->stage_bytes = (g->box_bytes + 127u) & ~127u;
+  int nst = (int)(avail / g->stage_bytes);
+  // TMA is latency-bound: keep >= ~96 KB in flight per SM when the stages are small
+  nst = std::min(nst, std::max(2, std::min(kConvMaxStages, (int)(98304u / g->stage_bytes))));
   if (nst < 2) { seunet_set_error("conv: shared memory budget exceeded"); return 1; }
   g->nstages = nst;
   g->smem_bytes = wregion + nst * g->stage_bytes + kBarBytes + 128u;
@@ -582,6 +667,8 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
   a.in_chunks_total = in_chunks_total; a.in_chunk_off = in_chunk_off;
   a.out_chunks_total = out_chunks_total; a.out_chunk_off = out_chunk_off;
   a.nstages = g.nstages; a.wslots = g.wslots; a.nsteps = g.nsteps;
+  a.pb = g.pb; a.nboxes = g.nboxes; a.plane16 = (uint32_t)HV; a.cdil = g.dil;
+  a.dbg = getenv("SEUNET_CONV_DBG") ? atoi(getenv("SEUNET_CONV_DBG")) : 0;   // developer experiments (profile build only)
   a.stage_bytes = g.stage_bytes; a.box_bytes = g.box_bytes; a.wchunk_bytes = g.wchunk_bytes;
   a.a_sbo = (uint32_t)lineW * 16u;
   a.b_lbo = (uint32_t)nkd * g.COUT * 16u;
@@ -593,7 +680,7 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
   a.out_scale = out_scale;
   a.accum_out = accum_out;
   a.out_real_chunks = out_real_chunks < 0 ? g.COUT / 8 : out_real_chunks;
-  const uint32_t a_lbo = (uint32_t)HV * 16u;
+  const uint32_t a_lbo = (uint32_t)g.pb * HV * 16u;   // the two K halves (8-channel planes) of a box are pb halo planes apart
   auto tapoff = [&](int t) { return (uint32_t)(((t / 3) * g.dil * lineW + (t % 3) * g.dil) * 16); };
   a.a_hi = (((a.a_sbo >> 4) & 0x3FFFu)) | (1u << 14);   // SBO | descriptor version (bit 46)
   a.b_hi = ((128u >> 4) & 0x3FFFu) | (1u << 14);
@@ -624,8 +711,9 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
   if (!enc) { seunet_set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)"); return 1; }
   cuuint64_t gdim[4] = {(cuuint64_t)8 * W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N * in_chunks_total};
   cuuint64_t gstr[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-  cuuint32_t box[4] = {(cuuint32_t)(8 * lineW), (cuuint32_t)(kConvTileH + 2 * halo), 1u, (cuuint32_t)(g.KC / 8)};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // a box spans pb planes of one parity class: extent pb * dstep along d, traversed with stride dstep
+  cuuint32_t box[4] = {(cuuint32_t)(8 * lineW), (cuuint32_t)(kConvTileH + 2 * halo), (cuuint32_t)(g.pb * a.dstep), (cuuint32_t)(g.KC / 8)};
+  cuuint32_t estr[4] = {1, 1, (cuuint32_t)a.dstep, 1};
   const CUtensorMapDataType dt = g.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUresult r = enc(&L->tmap, dt, 4, const_cast<void*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -642,11 +730,26 @@ static int conv_launch_t(const ConvLaunch& L, cudaStream_t st) {
   int dev = 0;
   SEUNET_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    SEUNET_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    SEUNET_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));   // + <= 4 KB static (s_run) <= 227 KB
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   conv_tc_kernel<COUT><<<L.grid, kConvThreads, L.g.smem_bytes, st>>>(L.tmap, L.a);
   SEUNET_CUDA_CHECK(cudaGetLastError());
+#ifdef SEUNET_CONV_PROFILE
+  {
+    static long long h[148 * 8];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_conv_prof, sizeof(h));
+    double s[8] = {0};
+    const int n = std::min(L.grid, 148);
+    for (int b = 0; b < n; ++b) for (int k = 0; k < 8; ++k) s[k] += (double)h[b * 8 + k] / n;
+    const double mmas = (double)L.a.numTiles / L.grid * L.a.nchunks * (kConvAccCols / COUT + 2 * L.a.dil) * L.a.nsteps;
+    fprintf(stderr, "[conv prof] COUT %d Cin %d k%d pb %d nboxes %d stages %d tiles %d: producer %.0f kclk (wait empty %.0f) | issuer %.0f kclk "
+            "(wait full %.0f, wait tmem %.0f, wait weights %.0f; %.1f clk per issued-plane MMA) | epilogue %.0f kclk (wait full %.0f)\n",
+            COUT, L.g.Cin, L.g.ksize, L.g.pb, L.g.nboxes, L.g.nstages, L.a.numTiles, s[0] / 1e3, s[1] / 1e3, s[2] / 1e3, s[3] / 1e3,
+            s[4] / 1e3, s[5] / 1e3, s[2] / std::max(1.0, mmas), s[6] / 1e3, s[7] / 1e3);
+  }
+#endif
   return 0;
 }
 

@@ -10,6 +10,7 @@ constexpr int kConvTableSteps = 8;  // steps of the table-driven issue mode (Cin
 constexpr int kConvTileH = 16;      // one UMMA M=128 block = 16 (h) x 8 (w) voxels of one d-plane
 constexpr int kConvTileW = 8;
 constexpr int kConvAccCols = 512;   // TMEM columns of the (single) accumulator stage: DT = 512/COUT output-plane slots
+constexpr int kConvGroups = 4;      // the slots are handed between issuer and epilogue in this many groups
 
 // Kernel arguments (passed by value as a __grid_constant__).
 struct ConvKArgs {
@@ -23,6 +24,10 @@ struct ConvKArgs {
   int in_chunks_total, in_chunk_off;
   int out_chunks_total, out_chunk_off;
   int nstages, wslots, nsteps;
+  int pb, nboxes;        // planes per TMA box (= ring stage) and boxes per (tile, channel chunk)
+  int dbg;               // developer experiment flags (only read by -DSEUNET_CONV_PROFILE builds)
+  int cdil;              // the conv's own dilation (1|2; tap offsets inside the halo tile), 0 for 1x1x1
+  uint32_t plane16;      // one halo plane inside a box, in 16-byte units
   uint32_t stage_bytes, box_bytes, wchunk_bytes;
   uint32_t a_sbo, b_lbo;
   uint32_t fmt;          // UMMA operand format of activations AND weights: 0 = f16, 1 = bf16
@@ -57,6 +62,7 @@ struct ConvGeom {
   int ksize;                // 3 or 1
   int dil;                  // conv dilation (3x3x3 only)
   int KC, nchunks, nsteps, wslots, nstages;
+  int pb, nboxes;           // planes per TMA box / boxes per tile
   bool paired;              // Cin == 8: two taps share one K=16 step
   int bf16;                 // operands (activations + packed weights) are bf16 (gradient operators)
   uint32_t stage_bytes, box_bytes, wchunk_bytes, smem_bytes;
