@@ -48,7 +48,12 @@ def test_nn_dataparallel_two_devices_matches_single_device(cuda_lib):
     m_1, o_1 = run(False)
     for (a0, a1, ga), (b0, b1, gb) in zip(o_dp, o_1):
         assert torch.equal(a0, b0) and torch.equal(a1, b1)       # per-sample statistics: batch split changes nothing
-        assert ga.keys() == gb.keys() and "dc62.conv1.weight" not in ga
+        # dc62 is dead code (SE_UNet.py:230): no gradient on a single device; under multi-device DataParallel autograd's
+        # Broadcast.backward materialises ZEROS for the replicas' unused tensors - in the reference exactly the same way
+        assert "dc62.conv1.weight" not in gb
+        if "dc62.conv1.weight" in ga:
+            assert ga.pop("dc62.conv1.weight").abs().max().item() == 0.0
+        assert ga.keys() == gb.keys()
         for n in ga:
             den = max(gb[n].norm().item(), 1e-12)
             # weight gradients are sums over the batch: the two replicas' partial sums are added on device 0 in another order
