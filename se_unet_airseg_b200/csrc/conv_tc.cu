@@ -130,35 +130,49 @@ __device__ __forceinline__ void issue_tile(IssueRing& r, const uint32_t a_lo_fir
   uint32_t dcol = tmem_base, idesc = idesc1, b_lo = b_lo_slot + (uint32_t)(2 * DIL * COUT);
   uint32_t a_plane = r.a_lo_st;
   int box_left = 0;
-#pragma unroll 1
-  for (int k = 0; k <= KMAX; ++k) {
+  const uint32_t kvspan = (uint32_t)(kv1 - kv0);
+  // One plane.  Everything that depends on the plane's position inside its group is a compile-time constant (the group loop
+  // below is unrolled), so the only run-time work besides the MMAs is the box bookkeeping and the in-volume test.
+  auto plane = [&](const int k, const bool grow, const bool shrink_after, const int commit_group) {
     if (box_left == 0) {
       mbar_wait(r.fbar, r.ph);      // TMA -> mbarrier -> MMA: ordered by the mbarrier itself
       a_plane = r.a_lo_st;
       box_left = pb;
     }
-    if (first_chunk && k < DT && (k % G) == 0) {
-      mbar_wait(tempty0 + 8u * (uint32_t)(k / G), tphase);
-      tc_fence_after();
-      umma_f16(tmem_base + k * COUT, zdesc, zdesc, idesc_clear, 0u);
-    }
-    if (k >= kv0 && k <= kv1)       // planes outside the volume arrive as zeros: nothing to add
+    if ((uint32_t)(k - kv0) <= kvspan)       // planes outside the volume arrive as zeros: nothing to add
       issue_mode<COUT, MODE>(dcol, a_plane, a_hi, b_lo, b_hi, idesc, j_step, b_step, jsteps, dlt);
-    if (last_chunk && k >= 2 * DIL && ((k - 2 * DIL) % G) == G - 1) umma_commit(tfull0 + 8u * (uint32_t)((k - 2 * DIL) / G));
+    if (commit_group >= 0 && last_chunk) umma_commit(tfull0 + 8u * (uint32_t)commit_group);
     // next plane: stacked kd blocks grow 1 -> 2 -> 3 at the start of the tile, shrink 3 -> 2 -> 1 at its end
     a_plane += plane16;
-    if (DIL == 1) {
-      if (k < 2) { idesc += kIdescNStep; b_lo -= COUT; }
-      else { dcol += COUT; if (k >= DT - 1) idesc -= kIdescNStep; }
-    } else {
-      dcol += COUT;
-    }
+    if (grow) { idesc += kIdescNStep; b_lo -= COUT; }
+    else { dcol += COUT; if (shrink_after) idesc -= kIdescNStep; }
     if (--box_left == 0 || k == KMAX) {
       umma_commit(r.fbar + 8u * kConvMaxStages);  // frees the activation stage when these MMAs retire
       box_left = 0;
       r.a_lo_st += stage16; r.fbar += 8u;
       if (++r.st == (uint32_t)nstages) { r.st = 0; r.ph ^= 1u; r.a_lo_st = a_lo_first; r.fbar = full0; }
     }
+  };
+#pragma unroll 1
+  for (int g = 0; g < kConvGroups; ++g) {
+    if (first_chunk) {
+      // acquire the group (drained by the epilogue) and clear it with one zero-operand UMMA
+      mbar_wait(tempty0 + 8u * (uint32_t)g, tphase);
+      tc_fence_after();
+      umma_f16(tmem_base + g * G * COUT, zdesc, zdesc, idesc_clear, 0u);
+    }
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int k = g * G + i;
+      if (DIL == 1)   // output plane k-2 is complete after plane k: group g-1 after the plane with i == 1
+        plane(k, g == 0 && i < 2, g == kConvGroups - 1 && i == G - 1, (i == 1 && g > 0) ? g - 1 : -1);
+      else            // pointwise: plane k only touches output plane k
+        plane(k, false, false, i == G - 1 ? g : -1);
+    }
+  }
+  if (DIL == 1) {     // the two halo planes behind the last output plane
+    plane(DT, false, true, -1);
+    plane(DT + 1, false, false, kConvGroups - 1);
   }
 }
 
