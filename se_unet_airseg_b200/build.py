@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libseunet_b200.so")
 STAMP = os.path.join(HERE, ".libseunet_b200.stamp")
-SOURCES = ["conv_tc.cu", "wgrad_tc.cu", "pointwise.cu", "pointwise2.cu", "window.cu", "backward.cu", "backward2.cu", "loss.cu", "postproc.cu", "plan.cu"]  # missing files are skipped
+SOURCES = ["conv_tc.cu", "wgrad_tc.cu", "pointwise.cu", "pointwise2.cu", "pointwise3.cu", "window.cu", "backward.cu", "backward2.cu", "loss.cu", "postproc.cu", "plan.cu"]  # missing files are skipped
 INCLUDE = os.path.join(HERE, "..", "include")
 
 NVCC_FLAGS = [

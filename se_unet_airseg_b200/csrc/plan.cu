@@ -6,6 +6,7 @@
 #include "wgrad_tc.cuh"
 #include "backward.cuh"
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -85,6 +86,9 @@ static const CatDesc kCat[6] = {
     {"dc42", 96, 32, 1, B_DC42IN, nullptr, B_D1F, 0, B_NONE},
 };
 enum CatId { C_EC33, C_EC63, C_EC93, C_EC123, C_DC22, C_DC42 };
+// Inference plans CAN fuse every CAT 1x1x1 conv into the apply pass of the LAST block that writes its concat (pointwise3.cu):
+// kSseFuse[i] = CAT block whose concat starts with SSE block i's output (chunk offset 0 of kCat[..].in_buf), or -1.
+static const int kSseFuse[18] = {-1, -1, C_EC33, -1, -1, C_EC63, -1, -1, C_EC93, -1, -1, C_EC123, -1, C_DC22, -1, C_DC42, -1, -1};
 
 // ---------------------------------------------------------------------------------------------
 // flat parameter table (state_dict order)
@@ -141,6 +145,10 @@ struct ConvSlot {
 
 struct seunet_plan {
   int N, D, H, W, in_ch, ncls, mode, device, num_sms;
+  // inference plans: CAT 1x1x1 convs fused into the producer's apply pass (pointwise3.cu).  OFF by default: measured on B200
+  // the fused pass (mma.sync, 2 blocks/SM) takes 127 us per window for ec3+ec33 against 49 + 63 us unfused, and its
+  // per-block statistics make the result depend on the batch size in the last bits.  SEUNET_CAT_FUSION=1 enables it.
+  bool fuse_cat = false;
   ParamTable pt;
   ConvSlot sse_conv[18], cat_conv[6];
   size_t buf_off[B_COUNT];
@@ -239,6 +247,7 @@ extern "C" int seunet_plan_create(seunet_plan_t** out, int batch, int D, int H, 
     delete p; return 1;
   }
   p->num_sms = prop.multiProcessorCount;
+  p->fuse_cat = getenv("SEUNET_CAT_FUSION") != nullptr && atoi(getenv("SEUNET_CAT_FUSION")) != 0;
 
   // --- conv geometry + packed weight image layout
   size_t wimg = 0;
@@ -414,6 +423,8 @@ extern "C" int seunet_pack_weights(seunet_plan_t* p, const float* params, seunet
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+static bool fuse_cat(const seunet_plan* p, int cat) { return p->mode == 0 && cat >= 0 && p->fuse_cat; }
+
 static int run_sse(seunet_plan* p, int i, const float* params, cudaStream_t st) {
   const SseDesc& s = kSse[i];
   ConvSlot& cs = p->sse_conv[i];
@@ -431,6 +442,21 @@ static int run_sse(seunet_plan* p, int i, const float* params, cudaStream_t st) 
   a.wcst = (const float*)(p->ws + p->wcst_off) + (size_t)i * p->N;
   a.T = (float*)(p->ws + (s.head == 0 ? p->T0_off[s.level] : p->T1_off[s.level]));
   a.t_init = (s.k % 3 == 0 && s.head == 0) || (s.head == 1 && s.k % 2 == 0);
+  if (fuse_cat(p, kSseFuse[i])) {
+    // the block output never leaves the SM: apply + CAT 1x1x1 conv in one pass (the CAT conv launch is skipped in run_cat)
+    const CatDesc& c = kCat[kSseFuse[i]];
+    ConvSlot& cc = p->cat_conv[kSseFuse[i]];
+    CatFuseArgs f;
+    memset(&f, 0, sizeof(f));
+    f.cat = (const act_t*)(p->ws + p->buf_off[c.in_buf]); f.cat_chunks = kBufs[c.in_buf].chunks; f.cat_real_chunks = (c.cin + 7) / 8;
+    f.w = params + cc.w_off; f.cin_real = c.cin;
+    f.kcat = ((c.cin + 15) / 16) * 16; f.nout = c.cout;
+    f.out = (act_t*)(p->ws + cc.raw_off); f.out_chunks = cc.g.COUT / 8;
+    f.out_stats = (double*)(p->ws + cc.stats_off); f.out_stats_c = cc.g.COUT;
+    if (launch_apply_sse_cat(s.cout, p->N, a, f, p->num_sms, st)) return 1;
+    p->mark((std::string("apply:") + s.name).c_str(), st);
+    return 0;
+  }
   if (s.out_buf != B_NONE) {
     a.dest = (act_t*)(p->ws + p->buf_off[s.out_buf]); a.dest_chunks = kBufs[s.out_buf].chunks; a.dest_off = s.out_off;
   }
@@ -442,7 +468,7 @@ static int run_sse(seunet_plan* p, int i, const float* params, cudaStream_t st) 
 static int run_cat(seunet_plan* p, int i, const float* params, const float* x, const int64_t* xs, cudaStream_t st) {
   const CatDesc& c = kCat[i];
   ConvSlot& cs = p->cat_conv[i];
-  if (conv_launch_run(cs.L, st)) return 1;
+  if (!fuse_cat(p, i) && conv_launch_run(cs.L, st)) return 1;   // fused plans: done inside the last producer's apply pass
   p->mark((std::string("conv:") + c.name).c_str(), st, 2.0 * p->N * p->vox(c.level) * cs.g.Cin_real * cs.g.Cout_real);
   CatArgs a;
   memset(&a, 0, sizeof(a));

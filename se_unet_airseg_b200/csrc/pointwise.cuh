@@ -1,6 +1,7 @@
 // Launchers for the HBM-bound kernels of the SE-UNet forward pass (all chunk-plane layout).
 #pragma once
 #include "common.cuh"
+#include <algorithm>
 
 constexpr int kMaxInCh = 2;     // reference callers use in_channel=2 (default ctor: 1)
 constexpr int kMomStride = 8;   // doubles per (level, sample): sum x_i (2), sum x_i x_j (3), pad
@@ -27,6 +28,17 @@ struct SseArgs {
   act_t* dest; int dest_chunks; int dest_off;  // gated activations, may be null
 };
 int launch_apply_sse(int C, int N, const SseArgs& a, cudaStream_t st);
+
+// Fused SSE apply + CAT 1x1x1 conv (pointwise3.cu; inference plans): the block's own C output channels are concat chunks
+// [0, C/8); chunks [C/8, cat_real_chunks) are read from the concat buffer; the conv output goes to `out` with statistics.
+struct CatFuseArgs {
+  const act_t* cat; int cat_chunks; int cat_real_chunks;   // concat buffer [n][cat_chunks][V][8]; chunks beyond cat_real_chunks are padding
+  const float* w; int cin_real;                            // CATConv weight fp32 [nout][cin_real]
+  int kcat, nout;                                          // padded K (multiple of 16) and output channels
+  act_t* out; int out_chunks;                              // raw conv output [n][out_chunks][V][8]
+  double* out_stats; int out_stats_c;                      // [n][out_stats_c][2], accumulated with atomics (zeroed by the caller)
+};
+int launch_apply_sse_cat(int C, int N, const SseArgs& a, const CatFuseArgs& f, int num_sms, cudaStream_t st);
 
 struct CatArgs {
   const act_t* raw; int raw_chunks;

@@ -104,6 +104,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
     }
   } else if (warp == 1) {
+    // One elected thread runs the whole issue loop (as in conv_tc.cu: re-converging the warp after every elected
+    // tcgen05.mma drains the tensor pipe's instruction queue; ptxas keeps the elect region on the uniform datapath).
+    if (elect_one_sync()) {
     uint32_t st = 0, ph = 0, any = 0;
     const uint32_t idesc = umma_idesc2(a.fmt_a, a.fmt_b, 1u, 1u, a.m64 ? 64 : 128, ntap * COUT);
     // A (X tile, 16x8 voxels, no halo) and B (ntap shifted dY tiles stacked along N): MN-major, m/n-groups = chunk planes
@@ -119,32 +122,31 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int po = p - dshift;
       if (++tw == a.tilesW) { tw = 0; if (++th == a.tilesH) { th = 0; if (++p == a.D) p = 0; } }
       if (po < 0 || po >= a.D) continue;
-      mbar_wait(fbar, ph);
-      tc_fence_after();
+      mbar_wait(fbar, ph);      // TMA -> mbarrier -> MMA: ordered by the mbarrier itself
       if (!any) {   // first tile plane of this CTA: the first MMA overwrites the accumulators
-        if (elect_one_sync()) {
+        {
           const uint64_t ad = ((uint64_t)desc_hi << 32) | a_lo_st, bd = ((uint64_t)desc_hi << 32) | b_lo_st;
           umma_f16(tmem_base, ad, bd, idesc, 0u);
         }
         any = 1;
 #pragma unroll 1
         for (int j = 1; j < ksteps; ++j)
-          if (elect_one_sync()) umma_f16_lohi(tmem_base, a_lo_st + 16u * j, desc_hi, b_lo_st + 16u * j, desc_hi, idesc);
+          umma_f16_lohi(tmem_base, a_lo_st + 16u * j, desc_hi, b_lo_st + 16u * j, desc_hi, idesc);
       } else {
 #pragma unroll 1
         for (int j8 = 0; j8 < ksteps; j8 += 8) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)   // two h-line segments of 8 voxels = 256 B per K=16 step
-            if (elect_one_sync()) umma_f16_lohi(tmem_base, a_lo_st + 16u * (j8 + j), desc_hi, b_lo_st + 16u * (j8 + j), desc_hi, idesc);
+            umma_f16_lohi(tmem_base, a_lo_st + 16u * (j8 + j), desc_hi, b_lo_st + 16u * (j8 + j), desc_hi, idesc);
         }
       }
-      if (elect_one_sync()) umma_commit(fbar + 64u);   // empty barrier of this stage
+      umma_commit(fbar + 64u);   // empty barrier of this stage
       a_lo_st += a_stage16; b_lo_st += b_stage16; fbar += 8u;
       if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; a_lo_st = a_lo_first; b_lo_st = b_lo_first; fbar = full_bar(0); }
     }
-    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(count_addr), "r"(any) : "memory");
-    __syncwarp();
-    if (elect_one_sync()) umma_commit(done_bar);
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(count_addr), "r"(any) : "memory");
+    umma_commit(done_bar);
+    }
     __syncwarp();
   } else {
     // epilogue: after ALL MMAs of this CTA, dump [ntap][128][COUT] fp32 to the partial buffer
