@@ -88,7 +88,9 @@ static const CatDesc kCat[6] = {
 enum CatId { C_EC33, C_EC63, C_EC93, C_EC123, C_DC22, C_DC42 };
 // Inference plans CAN fuse every CAT 1x1x1 conv into the apply pass of the LAST block that writes its concat (pointwise3.cu):
 // kSseFuse[i] = CAT block whose concat starts with SSE block i's output (chunk offset 0 of kCat[..].in_buf), or -1.
-static const int kSseFuse[18] = {-1, -1, C_EC33, -1, -1, C_EC63, -1, -1, C_EC93, -1, -1, C_EC123, -1, C_DC22, -1, C_DC42, -1, -1};
+// Only the 32-channel blocks (ec3 at full, dc4 at half resolution) are fused: the 64-channel variants of the pass need the whole
+// register file of an SM for one block and measured no faster than apply + tcgen05 conv (ec6 33.4 vs 15.1 + 18.0 us per window).
+static const int kSseFuse[18] = {-1, -1, C_EC33, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, C_DC42, -1, -1};
 
 // ---------------------------------------------------------------------------------------------
 // flat parameter table (state_dict order)
@@ -145,10 +147,8 @@ struct ConvSlot {
 
 struct seunet_plan {
   int N, D, H, W, in_ch, ncls, mode, device, num_sms;
-  // inference plans: CAT 1x1x1 convs fused into the producer's apply pass (pointwise3.cu).  OFF by default: measured on B200
-  // the fused pass (mma.sync, 2 blocks/SM) takes 127 us per window for ec3+ec33 against 49 + 63 us unfused, and its
-  // per-block statistics make the result depend on the batch size in the last bits.  SEUNET_CAT_FUSION=1 enables it.
-  bool fuse_cat = false;
+  // inference plans: CAT 1x1x1 convs fused into the producer's apply pass (pointwise3.cu); SEUNET_CAT_FUSION=0 disables it
+  bool fuse_cat = true;
   ParamTable pt;
   ConvSlot sse_conv[18], cat_conv[6];
   size_t buf_off[B_COUNT];
@@ -247,7 +247,7 @@ extern "C" int seunet_plan_create(seunet_plan_t** out, int batch, int D, int H, 
     delete p; return 1;
   }
   p->num_sms = prop.multiProcessorCount;
-  p->fuse_cat = getenv("SEUNET_CAT_FUSION") != nullptr && atoi(getenv("SEUNET_CAT_FUSION")) != 0;
+  p->fuse_cat = getenv("SEUNET_CAT_FUSION") == nullptr || atoi(getenv("SEUNET_CAT_FUSION")) != 0;
 
   // --- conv geometry + packed weight image layout
   size_t wimg = 0;
@@ -423,7 +423,11 @@ extern "C" int seunet_pack_weights(seunet_plan_t* p, const float* params, seunet
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-static bool fuse_cat(const seunet_plan* p, int cat) { return p->mode == 0 && cat >= 0 && p->fuse_cat; }
+static bool fuse_cat(const seunet_plan* p, int cat) {
+  if (p->mode != 0 || cat < 0 || !p->fuse_cat) return false;
+  for (int i = 0; i < 18; ++i) if (kSseFuse[i] == cat) return true;   // some block's apply pass computes this CAT conv
+  return false;
+}
 
 static int run_sse(seunet_plan* p, int i, const float* params, cudaStream_t st) {
   const SseDesc& s = kSse[i];
