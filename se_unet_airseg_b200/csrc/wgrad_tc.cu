@@ -10,9 +10,14 @@
 //     traffic; its accumulator rows live in TMEM lanes (r/16)*32 + r%16, measured); planes beyond Cin read junk whose
 //     rows are never used,
 //     N = Cout (16/32/64), K = 16 voxels (two h lines of the 16x8 tile) -> 8 MMAs per (tile plane, tap).
-//   * A pass fixes (kd, kh) - 9 passes for 3x3x3 - and keeps the three kw accumulators [128 x 3*Cout] in TMEM for
-//     the whole kernel: the accumulation over ALL voxels of the CTA's tile planes happens inside TMEM (fp32).
-//     1x1x1 convs use one pass per block of 128 input channels.
+//   * The three kw taps are stacked along N (three w-shifted dY boxes), and as many kh taps as fit are stacked along M
+//     (round 2): the A tile holds nkh h-shifted copies of the X box back to back - the chunk-plane stride stays uniform
+//     across the copies - so ONE M = 64/128 instruction covers nkh * 3 taps: nkh = 3 for Cin <= 40, 2 for Cin <= 64,
+//     1 above.  The kernel is bound by the NUMBER of MMAs (K is only 16 voxels; an M=128 instruction costs >= ~48 cycles
+//     whatever M and N are), so the full-resolution layers (Cin <= 32) need 3x fewer of them.
+//   * A pass fixes kd and a group of nkh kh taps - 3, 6 or 9 passes for 3x3x3 - and keeps its accumulators
+//     [nkh*Cin x 3*Cout] in TMEM for the whole kernel: the accumulation over ALL voxels of the CTA's tile planes happens
+//     inside TMEM (fp32).  1x1x1 convs use one pass per block of 128 input channels.
 //   * grid = npass * ctas_per_pass persistent CTAs; each writes its partial [taps][128][Cout] once; a small
 //     reduction kernel sums the partials in a fixed order (deterministic) into the flat fp32 gradient.
 //   * both operands use the activation storage type (tcgen05 kind::f16 faults on mixed f16 x bf16 operands, measured);
@@ -59,12 +64,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   const int pass = blockIdx.x / a.ctas_per_pass;
   const int rank = blockIdx.x % a.ctas_per_pass;
-  // 3x3x3: pass = kd*3 + kh; 1x1x1: pass = block of 128 input channels
-  const int kd = a.ksize == 3 ? pass / 3 : 1;
-  const int kh = a.ksize == 3 ? pass % 3 : 1;
+  // 3x3x3: pass = kd * npkh + (group of nkh kh taps); 1x1x1: pass = block of 128 input channels
+  const int kd = a.ksize == 3 ? pass / a.npkh : 1;
+  const int kh0 = a.ksize == 3 ? (pass % a.npkh) * a.nkh : 1;
+  const int nkh = a.ksize == 3 ? min(a.nkh, 3 - kh0) : 1;   // (the last group of a 2 + 1 split holds one tap: its second M half is junk)
   const int ntap = a.ksize == 3 ? 3 : 1;
   const int x_chunk = a.x_chunk_off + (a.ksize == 3 ? 0 : pass * 16);
-  const int dshift = (kd - 1) * a.dil, hshift = (kh - 1) * a.dil;
+  const int dshift = (kd - 1) * a.dil;
 
   // Each CTA of a pass walks a CONTIGUOUS range of tile planes; the (w, h, plane, sample) coordinates are advanced with
   // carries - the single-thread producer and issuer loops are issue-bound, and four runtime integer divisions per tile
@@ -87,7 +93,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     if (lane == 0) {
       uint32_t st = 0, ph = 0;
       Walk w = walk_init(tp_begin);
-      const uint32_t tx_bytes = a.x_box_bytes + ntap * a.dy_box_bytes;
+      const uint32_t tx_bytes = nkh * a.x_box_bytes + ntap * a.dy_box_bytes;
       const int kw0 = ntap == 3 ? 1 : 0;
       for (int tp = tp_begin; tp < tp_end; ++tp, walk_next(w)) {
         // tile plane `p` indexes the INPUT plane; it pairs with output-gradient plane p - dshift
@@ -96,10 +102,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int w0 = w.tw * a.tw, h0 = w.th * 16;
         mbar_wait(empty_bar(st), ph ^ 1u);
         mbar_expect_tx(full_bar(st), tx_bytes);
-        tma_load_4d(x_addr + st * a.x_stage_bytes, &tmap_x, full_bar(st), 8 * w0, h0, w.p, w.n * a.x_chunks_total + x_chunk);
-        for (int kw = 0; kw < ntap; ++kw)   // dY shifted against the taps: X[u] pairs with dY[u - shift(kd,kh,kw)]
+        // dW[tap] = sum_v X[v + shift(tap)] dY[v]: the kh shift is applied to the X copies (stacked along M), the kw shift
+        // to the dY copies (stacked along N), the kd shift to the plane pairing
+        for (int k = 0; k < nkh; ++k)
+          tma_load_4d(x_addr + st * a.x_stage_bytes + k * a.x_box_bytes, &tmap_x, full_bar(st), 8 * w0,
+                      h0 + (a.ksize == 3 ? (kh0 + k - 1) * a.dil : 0), w.p, w.n * a.x_chunks_total + x_chunk);
+        for (int kw = 0; kw < ntap; ++kw)
           tma_load_4d(dy_addr + st * a.dy_stage_bytes + kw * a.dy_box_bytes, &tmap_dy, full_bar(st),
-                      8 * (w0 - (kw - kw0) * a.dil), h0 - hshift, po, w.n * a.dy_chunks_total + a.dy_chunk_off);
+                      8 * (w0 - (kw - kw0) * a.dil), h0, po, w.n * a.dy_chunks_total + a.dy_chunk_off);
         if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
       }
     }
@@ -179,16 +189,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
-// dW[co][ci][kd][kh][kw] = sum_r partial[pass(kd,kh) or ci-block][r][kw][ci][co]   (fixed summation order)
+// dW[co][ci][kd][kh][kw] = sum_r partial[pass(kd, kh group) or ci-block][r][kw][(kh in group,) ci][co]   (fixed summation order)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cin, int Cout, int COUT,
-                                    int ksize, int ctas_per_pass, const float* __restrict__ inv_scale, int m64) {
+                                    int ksize, int ctas_per_pass, const float* __restrict__ inv_scale, int m64, int nkh, int npkh,
+                                    int x_rows) {
   const float mul = inv_scale ? inv_scale[0] : 1.f;
   const int K3 = ksize * ksize * ksize;
   const int total = Cout * Cin * K3;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int tap = i % K3, ci = (i / K3) % Cin, co = i / (K3 * Cin);
     int pass, kw, row;
-    if (ksize == 3) { pass = tap / 3; kw = tap % 3; row = ci; }
+    if (ksize == 3) {
+      const int kd = tap / 9, kh = (tap / 3) % 3;
+      pass = kd * npkh + kh / nkh; kw = tap % 3; row = (kh % nkh) * x_rows + ci;
+    }
     else { pass = ci / 128; kw = 0; row = ci % 128; }
     // UMMA M=64 accumulators use 16 TMEM lanes of each of the four 32-lane sub-partitions
     if (m64 == 1) row = (row >> 4) * 32 + (row & 15);
@@ -233,7 +247,12 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   if (Cout > 64 || (ksize != 1 && ksize != 3)) { seunet_set_error("wgrad: unsupported shape"); return 1; }
   if (ksize == 3 && Cin > 128) { seunet_set_error("wgrad: 3x3x3 with Cin > 128 unsupported"); return 1; }
   const int halo = ksize == 3 ? dil : 0;
-  const int npass = ksize == 3 ? 9 : (Cin + 127) / 128;
+  // kh taps stacked along M: as many h-shifted copies of the X box as fit 128 accumulator rows
+  const int xpl_all = std::min(16, (Cin + 7) / 8);
+  a.nkh = ksize == 3 ? (3 * xpl_all <= 16 ? 3 : (2 * xpl_all <= 16 ? 2 : 1)) : 1;
+  if (getenv("SEUNET_WG_NKH")) a.nkh = std::max(1, std::min(a.nkh, atoi(getenv("SEUNET_WG_NKH"))));   // developer A/B knob
+  a.npkh = (3 + a.nkh - 1) / a.nkh;
+  const int npass = ksize == 3 ? 3 * a.npkh : (Cin + 127) / 128;
   a.N = N; a.D = D; a.H = H; a.W = W;
   // Tile width: the per-stage costs (4 TMA instructions, barrier round trip, loop bookkeeping of the single-thread
   // producer/issuer) dominate narrow layers, so a stage covers as many voxels as ~100 KB of shared memory allow
@@ -241,7 +260,7 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   {
     const int coutp = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : 64);
     const int xpl = std::min(16, (Cin + 7) / 8);
-    const uint32_t per8 = 2048u * xpl + (ksize == 3 ? 3u : 1u) * 2048u * (coutp / 8);   // stage bytes at tw = 8
+    const uint32_t per8 = 2048u * xpl * a.nkh + (ksize == 3 ? 3u : 1u) * 2048u * (coutp / 8);   // stage bytes at tw = 8
     int tw = 8;
     static const uint32_t cap_kb = getenv("SEUNET_WG_STAGE_KB") ? (uint32_t)atoi(getenv("SEUNET_WG_STAGE_KB")) : 100u;
     while (tw < 32 && per8 * (tw * 2 / 8) <= cap_kb * 1024u && W >= tw * 2) tw *= 2;
@@ -260,7 +279,8 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   a.dy_chunks_total = dy_chunks_total; a.dy_chunk_off = dy_chunk_off;
   a.x_plane_bytes = 256u * a.tw;   // 16 x tw voxels x 16 B, no halo: the tap shifts are applied to dY
   a.x_box_bytes = a.x_plane_bytes * xplanes;
-  a.x_stage_bytes = (a.x_box_bytes + 127u) & ~127u;
+  a.x_stage_bytes = a.nkh * a.x_box_bytes;   // nkh copies back to back (a multiple of 2 KB)
+  a.x_rows = xplanes * 8;
   a.dy_box_bytes = a.x_plane_bytes * (L->COUT / 8);
   a.dy_stage_bytes = (ksize == 3 ? 3u : 1u) * a.dy_box_bytes;
   int nst = (int)((200u * 1024u) / (a.x_stage_bytes + a.dy_stage_bytes));
@@ -276,7 +296,7 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   if (L->smem_bytes > 224u * 1024u) { seunet_set_error("wgrad: shared memory budget exceeded (%u)", L->smem_bytes); return 1; }
   a.partial = partial;
   a.fmt_a = x_bf16 ? 1u : (uint32_t)SEUNET_UMMA_FMT;
-  a.m64 = (ksize == 3 ? Cin <= 64 : (Cin <= 64)) ? 1 : 0;   // UMMA M=64 when 8 chunk planes cover all input channels
+  a.m64 = a.nkh * xplanes <= 8 ? 1 : 0;   // UMMA M=64 when 8 chunk planes cover all (stacked) input rows
   a.fmt_b = a.fmt_a;  // tcgen05 kind::f16 requires A and B in the SAME format (mixed f16 x bf16 is an illegal instruction)
   if (geometry_only) return 0;
   if (ksize == 1 && x_chunk_off + npass * 16 > x_chunks_total + 15) { seunet_set_error("wgrad: bad 1x1 channel blocks"); return 1; }
@@ -323,7 +343,8 @@ int wgrad_launch_run(const WgradLaunch& L, float* dw, const float* inv_scale, cu
   if (rc) return rc;
   const int total = L.Cout * L.Cin * L.ksize * L.ksize * L.ksize;
   wgrad_reduce_kernel<<<std::min((total + 255) / 256, 592), 256, 0, st>>>(L.a.partial, dw, L.Cin, L.Cout, L.COUT, L.ksize,
-                                                                           L.a.ctas_per_pass, inv_scale, L.a.m64);
+                                                                           L.a.ctas_per_pass, inv_scale, L.a.m64, L.a.nkh, L.a.npkh,
+                                                                           L.a.x_rows);
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -12,7 +12,9 @@ struct WgradKArgs {
   int x_chunks_total, x_chunk_off, dy_chunks_total, dy_chunk_off;
   uint32_t x_plane_bytes, x_box_bytes, x_stage_bytes, dy_box_bytes, dy_stage_bytes, bar_off;
   uint32_t fmt_a, fmt_b;
-  int m64;             // UMMA M=64 (Cin <= 64): halves the shared-memory traffic of the A operand
+  int m64;             // UMMA M=64 (stacked input rows <= 64): halves the shared-memory traffic of the A operand
+  int nkh, npkh;       // kh taps stacked along M per pass (h-shifted copies of the X box), passes per kd = ceil(3 / nkh)
+  int x_rows;          // accumulator rows per kh copy (chunk planes of the X box * 8)
   float* partial;
 };
 
