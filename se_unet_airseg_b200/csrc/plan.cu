@@ -391,9 +391,11 @@ extern "C" int seunet_plan_bind(seunet_plan_t* p, void* workspace, void* wimg, s
     const SseDesc& s = kSse[i];
     ConvSlot& cs = p->sse_conv[i];
     const Dims d = p->dims(s.level);
+    // inference plans do not store the zero padding planes of the raw output (ec1: 8 real channels in a COUT = 16 tile; ncu showed
+    // the conv writing as many DRAM bytes as ec2); training plans keep them defined for the debug/test accessors
     if (conv_launch_init(&cs.L, cs.g, d.N, d.D, d.H, d.W, p->ws + p->buf_off[s.in_buf], kBufs[s.in_buf].chunks, s.in_off,
                          p->ws + cs.raw_off, cs.g.COUT / 8, 0, (double*)(p->ws + cs.stats_off), p->wimg + cs.wimg_off,
-                         p->num_sms))
+                         p->num_sms, 0, p->mode == 0 ? (cs.g.Cout_real + 7) / 8 : -1))
       return 1;
   }
   for (int i = 0; i < 6; ++i) {
@@ -472,8 +474,10 @@ static int run_sse(seunet_plan* p, int i, const float* params, cudaStream_t st) 
 static int run_cat(seunet_plan* p, int i, const float* params, const float* x, const int64_t* xs, cudaStream_t st) {
   const CatDesc& c = kCat[i];
   ConvSlot& cs = p->cat_conv[i];
-  if (!fuse_cat(p, i) && conv_launch_run(cs.L, st)) return 1;   // fused plans: done inside the last producer's apply pass
-  p->mark((std::string("conv:") + c.name).c_str(), st, 2.0 * p->N * p->vox(c.level) * cs.g.Cin_real * cs.g.Cout_real);
+  if (!fuse_cat(p, i)) {   // fused plans: the contraction was done inside the last producer's apply pass (no launch, no timing entry)
+    if (conv_launch_run(cs.L, st)) return 1;
+    p->mark((std::string("conv:") + c.name).c_str(), st, 2.0 * p->N * p->vox(c.level) * cs.g.Cin_real * cs.g.Cout_real);
+  }
   CatArgs a;
   memset(&a, 0, sizeof(a));
   a.raw = (const act_t*)(p->ws + cs.raw_off); a.raw_chunks = cs.g.COUT / 8;
