@@ -189,6 +189,180 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Version 3 (round 2), 3x3x3 layers with Cout <= 32: the three kd taps share ONE walk over the volume.
+// ncu on the pass-per-(kd, kh-group) kernel above (profiles/r02_wgrad_ncu_b8.txt): dc5 moves 45 GB from L2 to shared memory
+// per 8-patch step (13 TB/s) and 12.9 GB from DRAM for 3.2 GB of operands - every pass re-reads X and dY.  Here a CTA walks
+// whole (h, w) tile COLUMNS along d and keeps the previous plane's X and dY stage alive, so plane p is loaded once and used
+// three times:   kd = 1: X_p x dY_p      kd = 2: X_p x dY_(p-dil)      kd = 0: X_(p-dil) x dY_p
+// into three accumulator sets [nkh*Cin x 3*Cout] (3 * 96 <= 512 TMEM columns - why Cout = 64 stays on the kernel above).
+// Dilation-2 layers walk the two plane parity classes as separate columns (inside a class the kd taps are neighbours).
+// A stage is released after the NEXT step's MMAs (or at the end of its column).  L2->SMEM traffic drops 3x; the MMA count is
+// unchanged, so the full-resolution layers end up MMA-count-bound (K = 16 voxels per instruction).
+// ---------------------------------------------------------------------------------------------
+template <int COUT>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                 const __grid_constant__ WgradKArgs a) {
+  constexpr int NCOLS = 3 * COUT;            // accumulator columns per kd set (three kw taps)
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t x_addr = smem_base;
+  const uint32_t dy_addr = smem_base + a.nstages * a.x_stage_bytes;
+  const uint32_t bar_addr = smem_base + a.bar_off;
+  auto full_bar = [&](int i) { return bar_addr + 8u * i; };
+  auto empty_bar = [&](int i) { return bar_addr + 8u * (8 + i); };
+  const uint32_t done_bar = bar_addr + 8u * 16;
+  const uint32_t tmem_slot_addr = bar_addr + 8u * 17;
+  const uint32_t count_addr = bar_addr + 8u * 18;
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < a.nstages; ++i) { mbar_init(full_bar(i), 1); mbar_init(empty_bar(i), 1); }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmap_x);
+    tma_prefetch_desc(&tmap_dy);
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot_addr, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot_addr));
+  tmem_base = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+  const int pass = blockIdx.x / a.ctas_per_pass;       // group of nkh kh taps
+  const int rank = blockIdx.x % a.ctas_per_pass;
+  const int kh0 = pass * a.nkh;
+  const int nkh = min(a.nkh, 3 - kh0);
+  const int dstep = a.dil;                             // plane distance of the kd taps = stride of a column's plane walk
+  const int c_begin = (int)((long long)rank * a.numCols / a.ctas_per_pass);
+  const int c_end = (int)((long long)(rank + 1) * a.numCols / a.ctas_per_pass);
+  struct Col { int n, h0, w0, par, P; };
+  auto col_decode = [&](int c) {
+    Col q;
+    q.par = c % dstep; c /= dstep;
+    q.w0 = (c % a.tilesW) * a.tw; c /= a.tilesW;
+    q.h0 = (c % a.tilesH) * 16; q.n = c / a.tilesH;
+    q.P = (a.D - q.par + dstep - 1) / dstep;
+    return q;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t st = 0, ph = 0;
+      const uint32_t tx_bytes = nkh * a.x_box_bytes + 3 * a.dy_box_bytes;
+      for (int c = c_begin; c < c_end; ++c) {
+        const Col q = col_decode(c);
+        for (int i = 0; i < q.P; ++i) {
+          const int p = q.par + dstep * i;
+          mbar_wait(empty_bar(st), ph ^ 1u);
+          mbar_expect_tx(full_bar(st), tx_bytes);
+          for (int k = 0; k < nkh; ++k)
+            tma_load_4d(x_addr + st * a.x_stage_bytes + k * a.x_box_bytes, &tmap_x, full_bar(st), 8 * q.w0,
+                        q.h0 + (kh0 + k - 1) * a.dil, p, q.n * a.x_chunks_total + a.x_chunk_off);
+          for (int kw = 0; kw < 3; ++kw)
+            tma_load_4d(dy_addr + st * a.dy_stage_bytes + kw * a.dy_box_bytes, &tmap_dy, full_bar(st),
+                        8 * (q.w0 - (kw - 1) * a.dil), q.h0, p, q.n * a.dy_chunks_total + a.dy_chunk_off);
+          if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      uint32_t st = 0, ph = 0, any = 0;     // any: bit kd set once accumulator set kd has been written
+      const uint32_t idesc = umma_idesc2(a.fmt_a, a.fmt_b, 1u, 1u, a.m64 ? 64 : 128, NCOLS);
+      const uint32_t desc_hi = ((a.x_plane_bytes >> 4) & 0x3FFFu) | (1u << 14);   // SBO = chunk-plane stride
+      const int ksteps = a.tw;
+      const uint32_t lbo_bits = ((128u >> 4) & 0x3FFFu) << 16;
+      const uint32_t a_lo0 = lbo_bits | ((x_addr & 0x3FFFFu) >> 4), b_lo0 = lbo_bits | ((dy_addr & 0x3FFFFu) >> 4);
+      const uint32_t a_stage16 = a.x_stage_bytes >> 4, b_stage16 = a.dy_stage_bytes >> 4;
+      // one kd group: ksteps MMAs of A (X stage sa) x B (dY stage sb) into accumulator set kd
+      auto group = [&](uint32_t sa, uint32_t sb, int kd) {
+        const uint32_t a_lo = a_lo0 + sa * a_stage16, b_lo = b_lo0 + sb * b_stage16;
+        const uint32_t d = tmem_base + (uint32_t)(kd * NCOLS);
+        {
+          const uint64_t ad = ((uint64_t)desc_hi << 32) | a_lo, bd = ((uint64_t)desc_hi << 32) | b_lo;
+          umma_f16(d, ad, bd, idesc, (any >> kd) & 1u);   // the very first MMA of a set overwrites it
+        }
+        any |= 1u << kd;
+#pragma unroll 1
+        for (int j = 1; j < ksteps; ++j) umma_f16_lohi(d, a_lo + 16u * j, desc_hi, b_lo + 16u * j, desc_hi, idesc);
+      };
+      for (int c = c_begin; c < c_end; ++c) {
+        const Col q = col_decode(c);
+        uint32_t prev = 0;
+        for (int i = 0; i < q.P; ++i) {
+          mbar_wait(full_bar(st), ph);
+          group(st, st, 1);
+          if (i > 0) {
+            group(st, prev, 2);      // X_p x dY_(p - dil)
+            group(prev, st, 0);      // X_(p - dil) x dY_p
+            umma_commit(empty_bar(prev));
+          }
+          if (i == q.P - 1) umma_commit(empty_bar(st));
+          prev = st;
+          if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
+        }
+      }
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(count_addr), "r"(any) : "memory");
+      umma_commit(done_bar);
+    }
+    __syncwarp();
+  } else {
+    // epilogue: after ALL MMAs of this CTA, dump [kd][kw][128][COUT] fp32 to the partial buffer
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    uint32_t any;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(any) : "r"(count_addr));
+    float* dst = a.partial + ((size_t)blockIdx.x * 9 * 128 + row) * COUT;
+#pragma unroll 1
+    for (int t = 0; t < 9; ++t) {          // t = kd * 3 + kw
+      const bool live = (any >> (t / 3)) & 1u;
+#pragma unroll 1
+      for (int cg = 0; cg < COUT / 16; ++cg) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + t * COUT + cg * 16, v);
+        tmem_ld_wait();
+        float4* o = reinterpret_cast<float4*>(dst + (size_t)t * 128 * COUT + cg * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 f;
+          f.x = live ? __uint_as_float(v[4 * i]) : 0.f; f.y = live ? __uint_as_float(v[4 * i + 1]) : 0.f;
+          f.z = live ? __uint_as_float(v[4 * i + 2]) : 0.f; f.w = live ? __uint_as_float(v[4 * i + 3]) : 0.f;
+          o[i] = f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// v3 partial layout: [pass (kh group)][cta][kd][kw][128 rows = (kh in group, ci)][COUT]
+__global__ void wgrad3_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cin, int Cout, int COUT,
+                                     int ctas_per_pass, const float* __restrict__ inv_scale, int m64, int nkh, int x_rows) {
+  const float mul = inv_scale ? inv_scale[0] : 1.f;
+  const int total = Cout * Cin * 27;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % 27, ci = (i / 27) % Cin, co = i / (27 * Cin);
+    const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+    const int pass = kh / nkh;
+    int row = (kh % nkh) * x_rows + ci;
+    if (m64 == 1) row = (row >> 4) * 32 + (row & 15);
+    float s = 0.f;
+    for (int r = 0; r < ctas_per_pass; ++r)
+      s += partial[(((size_t)(pass * ctas_per_pass + r) * 9 + kd * 3 + kw) * 128 + row) * COUT + co];
+    dw[i] = s * mul;
+  }
+}
+
 // dW[co][ci][kd][kh][kw] = sum_r partial[pass(kd, kh group) or ci-block][r][kw][(kh in group,) ci][co]   (fixed summation order)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int Cin, int Cout, int COUT,
                                     int ksize, int ctas_per_pass, const float* __restrict__ inv_scale, int m64, int nkh, int npkh,
@@ -234,7 +408,7 @@ size_t wgrad_partial_bytes(int Cin, int Cout, int ksize, int num_sms) {
   WgradLaunch L;
   if (wgrad_launch_init(&L, 1, 16, 16, 8, Cin, Cout, ksize, 1, nullptr, (Cin + 7) / 8, 0, 0, nullptr, 8, 0, nullptr, num_sms, true))
     return 0;
-  return (size_t)L.grid * (ksize == 3 ? 3 : 1) * 128 * L.COUT * sizeof(float);
+  return (size_t)L.grid * (L.a.v3 ? 9 : (ksize == 3 ? 3 : 1)) * 128 * L.COUT * sizeof(float);
 }
 
 int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int Cout, int ksize, int dil,
@@ -251,8 +425,12 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   const int xpl_all = std::min(16, (Cin + 7) / 8);
   a.nkh = ksize == 3 ? (3 * xpl_all <= 16 ? 3 : (2 * xpl_all <= 16 ? 2 : 1)) : 1;
   if (getenv("SEUNET_WG_NKH")) a.nkh = std::max(1, std::min(a.nkh, atoi(getenv("SEUNET_WG_NKH"))));   // developer A/B knob
+  // version 3 (kd taps merged into one walk, see wgrad3_tc_kernel): 3x3x3 layers whose nine accumulator blocks fit TMEM
+  static const bool v3_enabled = !(getenv("SEUNET_WG_V3") && atoi(getenv("SEUNET_WG_V3")) == 0);   // developer A/B knob
+  a.v3 = (ksize == 3 && L->COUT <= 32 && v3_enabled) ? 1 : 0;
+  if (a.v3 && a.nkh == 2) a.nkh = 1;   // Cin = 64: one kh tap per pass keeps the stage at 40 KB (5 stages; 56 KB stages would leave one in flight)
   a.npkh = (3 + a.nkh - 1) / a.nkh;
-  const int npass = ksize == 3 ? 3 * a.npkh : (Cin + 127) / 128;
+  const int npass = ksize == 3 ? (a.v3 ? a.npkh : 3 * a.npkh) : (Cin + 127) / 128;
   a.N = N; a.D = D; a.H = H; a.W = W;
   // Tile width: the per-stage costs (4 TMA instructions, barrier round trip, loop bookkeeping of the single-thread
   // producer/issuer) dominate narrow layers, so a stage covers as many voxels as ~100 KB of shared memory allow
@@ -263,11 +441,13 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
     const uint32_t per8 = 2048u * xpl * a.nkh + (ksize == 3 ? 3u : 1u) * 2048u * (coutp / 8);   // stage bytes at tw = 8
     int tw = 8;
     static const uint32_t cap_kb = getenv("SEUNET_WG_STAGE_KB") ? (uint32_t)atoi(getenv("SEUNET_WG_STAGE_KB")) : 100u;
-    while (tw < 32 && per8 * (tw * 2 / 8) <= cap_kb * 1024u && W >= tw * 2) tw *= 2;
+    const uint32_t cap = a.v3 ? 40u * 1024u : cap_kb * 1024u;   // v3 keeps one extra stage alive: smaller stages, deeper ring
+    while (tw < 32 && per8 * (tw * 2 / 8) <= cap && W >= tw * 2) tw *= 2;
     a.tw = tw;
   }
   a.tilesW = (W + a.tw - 1) / a.tw; a.tilesH = (H + 15) / 16;
   a.numTilePlanes = N * D * a.tilesH * a.tilesW;
+  a.numCols = N * a.tilesH * a.tilesW * (halo == 2 ? 2 : 1);   // v3: (sample, h tile, w tile, plane parity class)
   a.dil = halo; a.ksize = ksize;
   a.lineW = 8 + 2 * halo;
   a.ctas_per_pass = std::max(1, num_sms / npass);
@@ -283,9 +463,9 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   a.x_rows = xplanes * 8;
   a.dy_box_bytes = a.x_plane_bytes * (L->COUT / 8);
   a.dy_stage_bytes = (ksize == 3 ? 3u : 1u) * a.dy_box_bytes;
-  int nst = (int)((200u * 1024u) / (a.x_stage_bytes + a.dy_stage_bytes));
-  nst = std::min(nst, 6);
-  if (nst < 2) { seunet_set_error("wgrad: shared memory budget exceeded"); return 1; }
+  int nst = (int)(((a.v3 ? 216u : 200u) * 1024u) / (a.x_stage_bytes + a.dy_stage_bytes));
+  nst = std::min(nst, a.v3 ? 8 : 6);
+  if (nst < (a.v3 ? 3 : 2)) { seunet_set_error("wgrad: shared memory budget exceeded"); return 1; }
   a.nstages = nst;
   uint32_t natural = nst * (a.x_stage_bytes + a.dy_stage_bytes);
   // junk rows: an M=128 A operand spans 16 chunk planes from the start of the LAST X stage
@@ -326,8 +506,13 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
 
 template <int COUT>
 static int wgrad_launch_t(const WgradLaunch& L, cudaStream_t st) {
-  SEUNET_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-  wgrad_tc_kernel<COUT><<<L.grid, kWgThreads, L.smem_bytes, st>>>(L.tmap_x, L.tmap_dy, L.a);
+  if (L.a.v3) {
+    SEUNET_CUDA_CHECK(cudaFuncSetAttribute(wgrad3_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    wgrad3_tc_kernel<COUT><<<L.grid, kWgThreads, L.smem_bytes, st>>>(L.tmap_x, L.tmap_dy, L.a);
+  } else {
+    SEUNET_CUDA_CHECK(cudaFuncSetAttribute(wgrad_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    wgrad_tc_kernel<COUT><<<L.grid, kWgThreads, L.smem_bytes, st>>>(L.tmap_x, L.tmap_dy, L.a);
+  }
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -342,6 +527,12 @@ int wgrad_launch_run(const WgradLaunch& L, float* dw, const float* inv_scale, cu
   }
   if (rc) return rc;
   const int total = L.Cout * L.Cin * L.ksize * L.ksize * L.ksize;
+  if (L.a.v3) {
+    wgrad3_reduce_kernel<<<std::min((total + 255) / 256, 592), 256, 0, st>>>(L.a.partial, dw, L.Cin, L.Cout, L.COUT, L.a.ctas_per_pass,
+                                                                              inv_scale, L.a.m64, L.a.nkh, L.a.x_rows);
+    SEUNET_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   wgrad_reduce_kernel<<<std::min((total + 255) / 256, 592), 256, 0, st>>>(L.a.partial, dw, L.Cin, L.Cout, L.COUT, L.ksize,
                                                                            L.a.ctas_per_pass, inv_scale, L.a.m64, L.a.nkh, L.a.npkh,
                                                                            L.a.x_rows);
