@@ -106,8 +106,14 @@ int launch_input_prep(const float* x, const long long* xs, const XOffsets& xo, i
 // =============================================================================================
 // (register caps chosen by A/B: C = 64 gains 17 % from three blocks per SM instead of two; the narrower variants need <= 64
 // registers for four blocks (C = 32) / 42 for six (C <= 16) - with fewer resident blocks they are 7-10 % slower)
+// VPT voxels per thread (round 2): ncu on the 8- and 16-channel instances showed 60-70 % issue-slot utilisation at 46 % of the DRAM
+// peak - with one 16/32-byte voxel per thread the per-block prologue (fp64 statistics, barrier) and the address arithmetic
+// outweigh the payload; those instances now loop over 4 voxels per thread (rolled: hoisting the loads of several voxels spilled).
+template <int C> struct SseVpt { static constexpr int value = C <= 16 ? 4 : 1; };
+
 template <int C, int GATES>
 __global__ void __launch_bounds__(256, C == 64 ? 3 : (C == 32 ? 4 : 6)) apply_sse_kernel(const __grid_constant__ SseArgs a) {
+  constexpr int VPT = SseVpt<C>::value;
   __shared__ __align__(16) float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -122,63 +128,69 @@ __global__ void __launch_bounds__(256, C == 64 ? 3 : (C == 32 ? 4 : 6)) apply_ss
     s_weff[c] = a.weff[(size_t)n * 64 + c];
   }
   __syncthreads();
-  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (v >= a.V) return;
   // per-channel constants come from shared memory as broadcast 128-bit loads (the kernel is issue-bound otherwise)
   auto ld8 = [](const float* sm, int k, float* r) {
     *reinterpret_cast<float4*>(r) = *reinterpret_cast<const float4*>(sm + k * 8);
     *reinterpret_cast<float4*>(r + 4) = *reinterpret_cast<const float4*>(sm + k * 8 + 4);
   };
-  float* tp = a.T + (size_t)n * a.V + v;
-  const float t_old = a.t_init ? 0.f : *tp;   // issued with the raw loads, not after the gate arithmetic
-  float e[C];
-  float g1 = 0.f;
-  Chunk8 in[C / 8];
+  float* tp0 = a.T + (size_t)n * a.V;
+  const float wcst = a.wcst[n];
+#pragma unroll 1
+  for (int u = 0; u < VPT; ++u) {
+    const long long v = (blockIdx.x * (long long)VPT + u) * blockDim.x + threadIdx.x;
+    if (v >= a.V) break;
+    float* tp = tp0 + v;
+    const float t_old = a.t_init ? 0.f : *tp;   // issued with the raw loads, not after the gate arithmetic
+    float e[C];
+    float g1 = 0.f;
+    Chunk8 in[C / 8];
 #pragma unroll
-  for (int k = 0; k < C / 8; ++k) in[k] = ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8);
-#pragma unroll
-  for (int k = 0; k < C / 8; ++k) {
-    float f[8], mean[8], rstd[8], wse[8];
-    chunk_to_floats(in[k], f);
-    ld8(s_mean, k, mean); ld8(s_rstd, k, rstd); ld8(s_wse, k, wse);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float t = lrelu_((f[i] - mean[i]) * rstd[i]);
-      e[k * 8 + i] = t;
-      g1 = fmaf(wse[i], t, g1);
-    }
-  }
-  g1 = sigmoidf_(g1);
-  if (GATES == 2) {
-    float g2 = 0.f;
+    for (int k = 0; k < C / 8; ++k) in[k] = ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8);
 #pragma unroll
     for (int k = 0; k < C / 8; ++k) {
-      float wse2[8];
-      ld8(s_wse2, k, wse2);
+      float f[8], mean[8], rstd[8], wse[8];
+      chunk_to_floats(in[k], f);
+      ld8(s_mean, k, mean); ld8(s_rstd, k, rstd); ld8(s_wse, k, wse);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { e[k * 8 + i] *= g1; g2 = fmaf(wse2[i], e[k * 8 + i], g2); }
+      for (int i = 0; i < 8; ++i) {
+        const float t = lrelu_((f[i] - mean[i]) * rstd[i]);
+        e[k * 8 + i] = t;
+        g1 = fmaf(wse[i], t, g1);
+      }
     }
-    g1 = sigmoidf_(g2);   // the second gate multiplies below
-  }
-  float t = a.wcst[n];
+    g1 = sigmoidf_(g1);
+    if (GATES == 2) {
+      float g2 = 0.f;
 #pragma unroll
-  for (int k = 0; k < C / 8; ++k) {
-    float weff[8];
-    ld8(s_weff, k, weff);
+      for (int k = 0; k < C / 8; ++k) {
+        float wse2[8];
+        ld8(s_wse2, k, wse2);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { e[k * 8 + i] *= g1; t = fmaf(weff[i], e[k * 8 + i], t); }
-  }
-  *tp = t_old + t;
-  if (a.dest) {
+        for (int i = 0; i < 8; ++i) { e[k * 8 + i] *= g1; g2 = fmaf(wse2[i], e[k * 8 + i], g2); }
+      }
+      g1 = sigmoidf_(g2);   // the second gate multiplies below
+    }
+    float t = wcst;
 #pragma unroll
-    for (int k = 0; k < C / 8; ++k)
-      st_chunk(a.dest + (((size_t)n * a.dest_chunks + a.dest_off + k) * a.V + v) * 8, floats_to_chunk(e + k * 8));
+    for (int k = 0; k < C / 8; ++k) {
+      float weff[8];
+      ld8(s_weff, k, weff);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { e[k * 8 + i] *= g1; t = fmaf(weff[i], e[k * 8 + i], t); }
+    }
+    *tp = t_old + t;
+    if (a.dest) {
+#pragma unroll
+      for (int k = 0; k < C / 8; ++k)
+        st_chunk(a.dest + (((size_t)n * a.dest_chunks + a.dest_off + k) * a.V + v) * 8, floats_to_chunk(e + k * 8));
+    }
   }
 }
 
 template <int C>
 static int launch_apply_sse_c(int N, const SseArgs& a, cudaStream_t st) {
-  dim3 grid((unsigned)((a.V + 255) / 256), N);
+  constexpr int VPB = 256 * SseVpt<C>::value;
+  dim3 grid((unsigned)((a.V + VPB - 1) / VPB), N);
   if (a.wse2) apply_sse_kernel<C, 2><<<grid, 256, 0, st>>>(a);
   else apply_sse_kernel<C, 1><<<grid, 256, 0, st>>>(a);
   SEUNET_CUDA_CHECK(cudaGetLastError());
