@@ -25,6 +25,7 @@
 //     reduction kernel divides out again.
 #include "wgrad_tc.cuh"
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <cstdlib>
 
@@ -239,15 +240,23 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   const int kh0 = pass * a.nkh;
   const int nkh = min(a.nkh, 3 - kh0);
   const int dstep = a.dil;                             // plane distance of the kd taps = stride of a column's plane walk
-  const int c_begin = (int)((long long)rank * a.numCols / a.ctas_per_pass);
-  const int c_end = (int)((long long)(rank + 1) * a.numCols / a.ctas_per_pass);
-  struct Col { int n, h0, w0, par, P; };
-  auto col_decode = [&](int c) {
+  // Work units = column segments: a column is cut into a.nseg runs of planes when there are too few columns to fill the
+  // CTAs (small batches).  A segment that does not start at the first plane of its class first loads the plane before it as
+  // a warm-up stage (no MMAs of its own, it only serves the two cross terms of the segment's first plane).
+  const int numUnits = a.numCols * a.nseg;
+  const int c_begin = (int)((long long)rank * numUnits / a.ctas_per_pass);
+  const int c_end = (int)((long long)(rank + 1) * numUnits / a.ctas_per_pass);
+  struct Col { int n, h0, w0, par, i0, i1, warm; };   // planes par + dstep * i, i in [i0, i1); warm: also load i0 - 1 first
+  auto col_decode = [&](int u) {
     Col q;
+    const int seg = u % a.nseg;
+    int c = u / a.nseg;
     q.par = c % dstep; c /= dstep;
     q.w0 = (c % a.tilesW) * a.tw; c /= a.tilesW;
     q.h0 = (c % a.tilesH) * 16; q.n = c / a.tilesH;
-    q.P = (a.D - q.par + dstep - 1) / dstep;
+    const int P = (a.D - q.par + dstep - 1) / dstep;
+    q.i0 = (int)((long long)seg * P / a.nseg); q.i1 = (int)((long long)(seg + 1) * P / a.nseg);
+    q.warm = (q.i0 > 0 && q.i1 > q.i0) ? 1 : 0;
     return q;
   };
 
@@ -257,7 +266,7 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const uint32_t tx_bytes = nkh * a.x_box_bytes + 3 * a.dy_box_bytes;
       for (int c = c_begin; c < c_end; ++c) {
         const Col q = col_decode(c);
-        for (int i = 0; i < q.P; ++i) {
+        for (int i = q.i0 - q.warm; i < q.i1; ++i) {
           const int p = q.par + dstep * i;
           mbar_wait(empty_bar(st), ph ^ 1u);
           mbar_expect_tx(full_bar(st), tx_bytes);
@@ -295,15 +304,17 @@ wgrad3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       for (int c = c_begin; c < c_end; ++c) {
         const Col q = col_decode(c);
         uint32_t prev = 0;
-        for (int i = 0; i < q.P; ++i) {
+        for (int i = q.i0 - q.warm; i < q.i1; ++i) {
           mbar_wait(full_bar(st), ph);
-          group(st, st, 1);
-          if (i > 0) {
-            group(st, prev, 2);      // X_p x dY_(p - dil)
-            group(prev, st, 0);      // X_(p - dil) x dY_p
-            umma_commit(empty_bar(prev));
+          if (i >= q.i0) {             // (the warm-up plane belongs to the previous segment: it only becomes `prev`)
+            group(st, st, 1);
+            if (i > 0) {
+              group(st, prev, 2);      // X_p x dY_(p - dil)
+              group(prev, st, 0);      // X_(p - dil) x dY_p
+              umma_commit(empty_bar(prev));
+            }
+            if (i == q.i1 - 1) umma_commit(empty_bar(st));
           }
-          if (i == q.P - 1) umma_commit(empty_bar(st));
           prev = st;
           if (++st == (uint32_t)a.nstages) { st = 0; ph ^= 1u; }
         }
@@ -448,10 +459,23 @@ int wgrad_launch_init(WgradLaunch* L, int N, int D, int H, int W, int Cin, int C
   a.tilesW = (W + a.tw - 1) / a.tw; a.tilesH = (H + 15) / 16;
   a.numTilePlanes = N * D * a.tilesH * a.tilesW;
   a.numCols = N * a.tilesH * a.tilesW * (halo == 2 ? 2 : 1);   // v3: (sample, h tile, w tile, plane parity class)
+  a.nseg = 1;                                                    // (set below once the pass count is known)
   a.dil = halo; a.ksize = ksize;
   a.lineW = 8 + 2 * halo;
   a.ctas_per_pass = std::max(1, num_sms / npass);
   L->grid = npass * a.ctas_per_pass;
+  if (a.v3) {
+    // >= 2 work units per CTA, segments of >= 8 planes (every extra segment costs one extra stage load)
+    // pick the segment count with the best (load balance) x (extra warm-up loads) product
+    const int P = std::max(1, D / std::max(1, halo));
+    double best = 1e30;
+    for (int ns = 1; ns <= std::max(1, std::min(16, P / 8)); ++ns) {
+      const double units = (double)a.numCols * ns;
+      const double per_cta = std::ceil(units / a.ctas_per_pass) / (units / a.ctas_per_pass);   // slowest CTA / average
+      const double cost = per_cta * (1.0 + (double)(ns - 1) / P);
+      if (cost < best - 1e-9) { best = cost; a.nseg = ns; }
+    }
+  }
   // planes per X box: the real channel planes of this pass (<= 16)
   const int cin_planes_total = (Cin + 7) / 8;
   const int xplanes = std::min(16, cin_planes_total);

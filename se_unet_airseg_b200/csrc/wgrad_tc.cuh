@@ -15,6 +15,7 @@ struct WgradKArgs {
   int m64;             // UMMA M=64 (stacked input rows <= 64): halves the shared-memory traffic of the A operand
   int nkh, npkh;       // kh taps stacked along M per pass (h-shifted copies of the X box), passes per kd = ceil(3 / nkh)
   int x_rows;          // accumulator rows per kh copy (chunk planes of the X box * 8)
+  int nseg;            // v3: segments (runs of planes) per column
   int v3, numCols;     // version 3 (kd taps merged into one walk along d): tile columns (sample, h tile, w tile, parity class)
   float* partial;
 };
