@@ -74,6 +74,16 @@ int seunet_forward(seunet_plan_t* plan, const float* x, const int64_t* x_strides
                    const float* params, const float* drop0, const float* drop1, float* pred0, float* pred1,
                    seunet_stream_t stream);
 
+/* One step of the sliding-window loop, prediction.py:102-106, for the `batch` windows of an inference (mode 0) plan:
+ *   p0, p = model(x_input); pred[window] += sigmoid(p)
+ * x / x_strides / x_offsets / params / drop0 / drop1 as in seunet_forward; starts = HOST [batch][3] window origins inside
+ * the (X,Y,Z) accumulator volume `acc` (32-bit fixed point, units of 2^-acc_log2, see seunet_window_accumulate).
+ * Equivalent to seunet_forward + seunet_window_accumulate(apply_sigmoid = 1) bit for bit, but p0 - which prediction.py
+ * discards - is not computed (no head-0 side branches), and p never reaches memory. */
+int seunet_forward_window(seunet_plan_t* plan, const float* x, const int64_t* x_strides, const int64_t* x_offsets,
+                          const float* params, const float* drop0, const float* drop1, const int* starts, uint32_t* acc,
+                          int X, int Y, int Z, int acc_log2, seunet_stream_t stream);
+
 /* Backward of SE_UNet.forward (autograd reached from loss.backward(), train.py:246/300/439/490/602) for a mode-1 plan
  * whose last seunet_forward used the same x / params / drop factors.  dpred0/dpred1: fp32 gradients w.r.t. the two
  * logit tensors [batch][1][D][H][W]; grads: flat fp32 gradient buffer in the parameter layout (overwritten).

@@ -29,6 +29,7 @@ SIGNATURES = {
     "seunet_plan_bind": (_i, [_vp, _vp, _vp, _vp]),
     "seunet_pack_weights": (_i, [_vp, _vp, _vp]),
     "seunet_forward": (_i, [_vp, _vp, _c.POINTER(_i64), _c.POINTER(_i64), _vp, _vp, _vp, _vp, _vp, _vp]),
+    "seunet_forward_window": (_i, [_vp, _vp, _c.POINTER(_i64), _c.POINTER(_i64), _vp, _vp, _vp, _c.POINTER(_i), _vp, _i, _i, _i, _i, _vp]),
     "seunet_backward": (_i, [_vp, _vp, _c.POINTER(_i64), _c.POINTER(_i64), _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "seunet_plan_set_timing": (_i, [_vp, _i]),
     "seunet_plan_timing_count": (_i, [_vp]),

@@ -2,6 +2,7 @@
 // Up^T is three 1-D adjoint passes (w, then h, then d) over shrinking tensors instead of one (2*2^l+1)^3 gather per voxel.
 #include "backward.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 __device__ __forceinline__ float axis_w1(int o, int j, int in_size, int out_size) {   // weight of source j in output o
   const float scale = out_size > 1 ? (float)(in_size - 1) / (float)(out_size - 1) : 0.f;
@@ -81,12 +82,164 @@ __global__ void __launch_bounds__(256) adjoint_axis_vec_kernel(const float4* __r
   out[(((long long)plane * A + a) * coarse + j) * inner4 + q] = acc;
 }
 
-// gsrc[n][C/8][sd] = Up2^T(gdst slice); tmp1 >= N*C*(2D*2H*W) floats, tmp2 >= N*C*(2D*H*W) floats
+// ---------------------------------------------------------------------------------------------------------------------
+// The same adjoint in ONE pass (round 2): the three 1-D passes above move 268 + 134 + 134 + 67 + 67 + 33 MB per 128^3 patch
+// for the 32-channel layer; only the first read and the last write are algorithmic.  A block owns TH source rows (all of W)
+// of one chunk plane and marches through the fine d-planes: the w pass reads the fine rows straight from global memory
+// (neighbouring threads share sectors through L1), the h pass runs out of shared memory, and the d pass is a ROLLING pair
+// of register accumulators (fine plane o feeds source planes i0(o) and i0(o)+1; a source plane is written when i0 moves
+// past it).  Same taps, weights and summation order as the three passes, so the result is bit-identical.
+// ---------------------------------------------------------------------------------------------------------------------
+struct AxisTaps { int first; float w[6]; int pad; };   // fine indices first .. first+5 feed source index j with weights w (zeros allowed)
+__device__ __forceinline__ AxisTaps axis_taps(int j, int coarse, int fine) {
+  const float inv = coarse > 1 ? (float)(fine - 1) / (float)(coarse - 1) : 0.f;
+  AxisTaps t;
+  t.first = max(0, (int)floorf((float)(j - 1) * inv));
+  t.pad = 0;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) t.w[c] = t.first + c < fine ? axis_w1(t.first + c, j, coarse, fine) : 0.f;
+  return t;
+}
+
+constexpr int kUbMaxItems = 2;   // (source row, w) positions per thread: TH * Ws <= 512
+
+__global__ void __launch_bounds__(256, 2) upsample2_bwd_fused_kernel(const float* __restrict__ gdst, long long sample_stride, long long plane_stride,
+                                                                     Dims sd, float* __restrict__ gsrc, int K, int TH, int dper) {
+  extern __shared__ __align__(32) uint8_t s_ub[];
+  const int Ws = sd.W, Hs = sd.H, Ds = sd.D, Wo = Ws * 2, Ho = Hs * 2, Do = Ds * 2;
+  AxisTaps* tabW = reinterpret_cast<AxisTaps*>(s_ub);           // [Ws]
+  AxisTaps* tabH = tabW + Ws;                                   // [TH]
+  float* R = reinterpret_cast<float*>(tabH + TH);               // [Hn][Ws][8]: fine rows of the current plane after the w pass
+  const int plane = blockIdx.z, n = plane / K, k = plane - n * K;
+  const int jh0 = blockIdx.y * TH, the = min(TH, Hs - jh0);
+  const int jd0 = blockIdx.x * dper, jd1 = min(Ds, jd0 + dper);
+  for (int t = threadIdx.x; t < Ws; t += blockDim.x) tabW[t] = axis_taps(t, Ws, Wo);
+  if (threadIdx.x < the) tabH[threadIdx.x] = axis_taps(jh0 + threadIdx.x, Hs, Ho);
+  __syncthreads();
+  const int ohlo = tabH[0].first, ohhi = min(Ho - 1, tabH[the - 1].first + 5), Hn = ohhi - ohlo + 1;
+  const int odlo = axis_taps(jd0, Ds, Do).first, odhi = min(Do - 1, axis_taps(jd1 - 1, Ds, Do).first + 5);
+  const float* gp = gdst + n * sample_stride + k * plane_stride;
+  float* op = gsrc + (size_t)plane * Ds * Hs * Ws * 8;
+  const float dscale = Do > 1 ? (float)(Ds - 1) / (float)(Do - 1) : 0.f;
+  // this thread's (source row, w) positions of the h / d passes
+  int jh_[kUbMaxItems], jw_[kUbMaxItems];
+  bool live[kUbMaxItems];
+#pragma unroll
+  for (int it = 0; it < kUbMaxItems; ++it) {
+    const int item = threadIdx.x + it * 256;
+    live[it] = item < the * Ws;
+    jh_[it] = live[it] ? item / Ws : 0;
+    jw_[it] = live[it] ? item - jh_[it] * Ws : 0;
+  }
+  float acc[2][kUbMaxItems][8];
+#pragma unroll
+  for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+    for (int it = 0; it < kUbMaxItems; ++it)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[sl][it][i] = 0.f;
+  int cur = (int)(dscale * (float)odlo);   // source plane of slot 0 (= i0 of the current fine plane)
+  auto flush0 = [&]() {                    // slot 0 is complete: write it (if it is one of this block's planes), shift the pair
+    if (cur >= jd0 && cur < jd1) {
+#pragma unroll
+      for (int it = 0; it < kUbMaxItems; ++it)
+        if (live[it]) st_grad8(op + (((size_t)cur * Hs + jh0 + jh_[it]) * Ws + jw_[it]) * 8, acc[0][it]);
+    }
+#pragma unroll
+    for (int it = 0; it < kUbMaxItems; ++it)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc[0][it][i] = acc[1][it][i]; acc[1][it][i] = 0.f; }
+    ++cur;
+  };
+  for (int od = odlo; od <= odhi; ++od) {
+    // ---- w pass: fine rows ohlo..ohhi of plane od -> R
+    const float* pl = gp + ((size_t)od * Ho + ohlo) * Wo * 8;
+    for (int item = threadIdx.x; item < Hn * Ws; item += blockDim.x) {
+      const int r = item / Ws, jw = item - r * Ws;
+      const AxisTaps t = tabW[jw];
+      const float* row = pl + ((size_t)r * Wo + t.first) * 8;
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        if (t.w[c] != 0.f) {
+          float v[8];
+          ld_grad8_cached(row + c * 8, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = fmaf(t.w[c], v[i], a[i]);
+        }
+      float4* rp = reinterpret_cast<float4*>(R + (size_t)item * 8);
+      rp[0] = make_float4(a[0], a[1], a[2], a[3]);
+      rp[1] = make_float4(a[4], a[5], a[6], a[7]);
+    }
+    __syncthreads();
+    // ---- h pass from shared memory, then the rolling d pass in registers
+    const int i0 = (int)(dscale * (float)od);
+    while (cur < i0) flush0();             // (block-uniform)
+    const float wa = axis_w1(od, cur, Ds, Do), wb = cur + 1 < Ds ? axis_w1(od, cur + 1, Ds, Do) : 0.f;
+#pragma unroll
+    for (int it = 0; it < kUbMaxItems; ++it) {
+      if (!live[it]) continue;
+      const AxisTaps t = tabH[jh_[it]];
+      const float* rp = R + ((size_t)(t.first - ohlo) * Ws + jw_[it]) * 8;
+      float pv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 6; ++c)
+        if (t.w[c] != 0.f) {
+          const float4 u0 = *reinterpret_cast<const float4*>(rp + (size_t)c * Ws * 8), u1 = *reinterpret_cast<const float4*>(rp + (size_t)c * Ws * 8 + 4);
+          pv[0] = fmaf(t.w[c], u0.x, pv[0]); pv[1] = fmaf(t.w[c], u0.y, pv[1]); pv[2] = fmaf(t.w[c], u0.z, pv[2]); pv[3] = fmaf(t.w[c], u0.w, pv[3]);
+          pv[4] = fmaf(t.w[c], u1.x, pv[4]); pv[5] = fmaf(t.w[c], u1.y, pv[5]); pv[6] = fmaf(t.w[c], u1.z, pv[6]); pv[7] = fmaf(t.w[c], u1.w, pv[7]);
+        }
+      if (wa != 0.f) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[0][it][i] = fmaf(wa, pv[i], acc[0][it][i]);
+      }
+      if (wb != 0.f) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[1][it][i] = fmaf(wb, pv[i], acc[1][it][i]);
+      }
+    }
+    __syncthreads();                       // R is overwritten by the next plane
+  }
+  flush0();
+  flush0();
+}
+
+static int upsample2_bwd_fused(const grad_t* gdst, int gdst_chunks, int gdst_off, int C, Dims sd, grad_t* gsrc, int num_sms, cudaStream_t st) {
+  const int K = C / 8, TH = sd.W <= 64 ? 8 : 4;
+  const long long Vo = (long long)sd.D * sd.H * sd.W * 8;
+  const size_t smem = (size_t)(sd.W + TH) * sizeof(AxisTaps) + (size_t)(2 * TH + 6) * sd.W * 32;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  SEUNET_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { seunet_set_error("upsample2_bwd: device index %d", dev); return 1; }
+  if (!attr_set[dev]) {
+    SEUNET_CUDA_CHECK(cudaFuncSetAttribute(upsample2_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_set[dev] = true;
+  }
+  const int htiles = (sd.H + TH - 1) / TH;
+  // enough blocks for two per SM: split the d range when the batch is small (each split re-reads <= 6 fine planes of halo)
+  const long long base = (long long)htiles * sd.N * K;
+  int dsplit = (int)std::min<long long>(std::max(1, sd.D / 4), std::max<long long>(1, (2LL * num_sms + base - 1) / base));
+  const int dper = (sd.D + dsplit - 1) / dsplit;
+  dsplit = (sd.D + dper - 1) / dper;
+  upsample2_bwd_fused_kernel<<<dim3((unsigned)dsplit, (unsigned)htiles, (unsigned)(sd.N * K)), 256, smem, st>>>(
+      gdst + (size_t)gdst_off * Vo * 8, (long long)gdst_chunks * Vo * 8, Vo * 8, sd, gsrc, K, TH, dper);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// gsrc[n][C/8][sd] = Up2^T(gdst slice); tmp1 >= N*C*(2D*2H*W) floats, tmp2 >= N*C*(2D*H*W) floats (three-pass fallback only)
 int launch_upsample2_bwd_sep(const grad_t* gdst, int gdst_chunks, int gdst_off, int C, Dims sd, grad_t* gsrc, float* tmp1, float* tmp2,
                              cudaStream_t st) {
   const int K = C / 8, Do = sd.D * 2, Ho = sd.H * 2, Wo = sd.W * 2;
   const long long Vo = (long long)Do * Ho * Wo;
   if (Do * Ho > 65535 || sd.N * K > 65535) return launch_upsample2_bwd(gdst, gdst_chunks, gdst_off, C, sd, gsrc, st);
+  static const bool three_pass = getenv("SEUNET_UPBWD_3PASS") != nullptr && atoi(getenv("SEUNET_UPBWD_3PASS")) != 0;   // A/B switch
+  if (!three_pass && sd.W <= 128 && sd.W * (sd.W <= 64 ? 8 : 4) <= 256 * kUbMaxItems && sd.D >= 2 && sd.H >= 2 && sd.W >= 2) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return upsample2_bwd_fused(gdst, gdst_chunks, gdst_off, C, sd, gsrc, sms, st);
+  }
   const float4* in0 = reinterpret_cast<const float4*>(gdst + (size_t)gdst_off * Vo * 8);
   auto blocks = [](long long n) { return (unsigned)((n + 255) / 256); };
   // along w: [Do*Ho][Wo -> W][2]   (a line has only 2*W float4 outputs: right-size the block)

@@ -111,17 +111,20 @@ __device__ __forceinline__ void st_grad8(grad_t* p, const float* f) {
 }
 #else
 typedef float grad_t;
+// One fp32 gradient chunk (8 channels of a voxel) is 32 bytes = one DRAM sector: sm_100 has 256-bit global loads/stores, so a
+// chunk is ONE instruction.  (ncu on the two-float4 version: 44 % "excessive sectors" in sse_bwd_a - each 128-bit half request
+// of a warp touches only half of every sector it fetches - and the L1 data pipeline, not DRAM, was the busy unit.)
 __device__ __forceinline__ void ld_grad8(const grad_t* p, float* f) {
-  const float4 a = __ldcs(reinterpret_cast<const float4*>(p)), b = __ldcs(reinterpret_cast<const float4*>(p) + 1);
-  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
 }
 __device__ __forceinline__ void ld_grad8_cached(const grad_t* p, float* f) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
-  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
 }
 __device__ __forceinline__ void st_grad8(grad_t* p, const float* f) {
-  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  asm volatile("st.global.v8.f32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]), "f"(f[4]), "f"(f[5]),
+               "f"(f[6]), "f"(f[7]), "l"(p) : "memory");
 }
 // p[0..7] += f[0..7] as two fire-and-forget vector reductions executed in L2: no read round trip through the SM
 #define SEUNET_HAVE_RED_GRAD8 1

@@ -149,6 +149,7 @@ struct seunet_plan {
   int N, D, H, W, in_ch, ncls, mode, device, num_sms;
   // inference plans: CAT 1x1x1 convs fused into the producer's apply pass (pointwise3.cu); SEUNET_CAT_FUSION=0 disables it
   bool fuse_cat = true;
+  bool skip_head0 = false;          // set for the duration of a seunet_forward_window call
   ParamTable pt;
   ConvSlot sse_conv[18], cat_conv[6];
   size_t buf_off[B_COUNT];
@@ -446,7 +447,7 @@ static int run_sse(seunet_plan* p, int i, const float* params, cudaStream_t st) 
   a.wse2 = s.gates == 2 ? params + p->pt.off(nm + ".conv_se2.weight") : nullptr;
   a.weff = (const float*)(p->ws + p->weff_off) + (size_t)i * p->N * 64;
   a.wcst = (const float*)(p->ws + p->wcst_off) + (size_t)i * p->N;
-  a.T = (float*)(p->ws + (s.head == 0 ? p->T0_off[s.level] : p->T1_off[s.level]));
+  a.T = (s.head == 0 && p->skip_head0) ? nullptr : (float*)(p->ws + (s.head == 0 ? p->T0_off[s.level] : p->T1_off[s.level]));
   a.t_init = (s.k % 3 == 0 && s.head == 0) || (s.head == 1 && s.k % 2 == 0);
   if (fuse_cat(p, kSseFuse[i])) {
     // the block output never leaves the SM: apply + CAT 1x1x1 conv in one pass (the CAT conv launch is skipped in run_cat)
@@ -506,12 +507,11 @@ static int run_cat(seunet_plan* p, int i, const float* params, const float* x, c
   return 0;
 }
 
-extern "C" int seunet_forward(seunet_plan_t* p, const float* x, const int64_t* xs, const int64_t* x_offsets,
-                              const float* params, const float* drop0, const float* drop1, float* pred0, float* pred1,
-                              seunet_stream_t stream) {
-  if (!p || !p->ws) { seunet_set_error("forward: plan not bound"); return 1; }
-  if (!x || !xs || !params || !drop0 || !drop1 || !pred0 || !pred1) { seunet_set_error("forward: null argument"); return 1; }
-  cudaStream_t st = (cudaStream_t)stream;
+struct WindowSink { uint32_t* acc; int X, Y, Z, acc_log2; const int* starts; };
+
+static int forward_impl(seunet_plan_t* p, const float* x, const int64_t* xs, const int64_t* x_offsets, const float* params,
+                        const float* drop0, const float* drop1, float* pred0, float* pred1, const WindowSink* sink,
+                        cudaStream_t st) {
   auto act = [&](int b) { return (act_t*)(p->ws + p->buf_off[b]); };
   memset(&p->xo, 0, sizeof(p->xo));
   if (x_offsets) {
@@ -562,9 +562,47 @@ extern "C" int seunet_forward(seunet_plan_t* p, const float* x, const int64_t* x
   h.bias0 = params + p->pt.off("dc0_0.bias");
   h.bias1 = params + p->pt.off("dc0_1.bias");
   h.pred0 = pred0; h.pred1 = pred1;
+  if (sink) {
+    h.acc = sink->acc; h.X = sink->X; h.Y = sink->Y; h.Z = sink->Z; h.acc_scale = (float)(1u << sink->acc_log2);
+    for (int n = 0; n < p->N; ++n)
+      for (int k = 0; k < 3; ++k) h.s[n][k] = sink->starts[n * 3 + k];
+  }
   if (launch_head(h, st)) return 1;
   p->mark("head", st);
   return 0;
+}
+
+extern "C" int seunet_forward(seunet_plan_t* p, const float* x, const int64_t* xs, const int64_t* x_offsets,
+                              const float* params, const float* drop0, const float* drop1, float* pred0, float* pred1,
+                              seunet_stream_t stream) {
+  if (!p || !p->ws) { seunet_set_error("forward: plan not bound"); return 1; }
+  if (!x || !xs || !params || !drop0 || !drop1 || !pred0 || !pred1) { seunet_set_error("forward: null argument"); return 1; }
+  p->skip_head0 = false;
+  return forward_impl(p, x, xs, x_offsets, params, drop0, drop1, pred0, pred1, nullptr, (cudaStream_t)stream);
+}
+
+// One sliding-window step of prediction.py:102-106 for a batch of windows: forward, sigmoid of the second output, += into the
+// volume accumulator.  prediction.py drops the first output (p0), so the whole deep-supervision head 0 - the folded side
+// branches of ec1..ec12 and their accumulators - is not computed, and the head-1 logits never reach memory: the head kernel
+// adds sigmoid(pred1) to the fixed-point accumulator directly (same arithmetic as seunet_window_accumulate).
+extern "C" int seunet_forward_window(seunet_plan_t* p, const float* x, const int64_t* xs, const int64_t* x_offsets,
+                                     const float* params, const float* drop0, const float* drop1, const int* starts,
+                                     uint32_t* acc, int X, int Y, int Z, int acc_log2, seunet_stream_t stream) {
+  if (!p || !p->ws) { seunet_set_error("forward_window: plan not bound"); return 1; }
+  if (!x || !xs || !params || !drop0 || !drop1 || !starts || !acc) { seunet_set_error("forward_window: null argument"); return 1; }
+  if (p->mode != 0) { seunet_set_error("forward_window: needs an inference plan (mode 0)"); return 1; }
+  if (p->N > kMaxWindowBatch) { seunet_set_error("forward_window: at most %d windows per call", kMaxWindowBatch); return 1; }
+  if (acc_log2 < 8 || acc_log2 > 30) { seunet_set_error("forward_window: acc_log2 %d out of range (8..30)", acc_log2); return 1; }
+  for (int n = 0; n < p->N; ++n)
+    for (int k = 0; k < 3; ++k) {
+      const int lim = k == 0 ? X - p->D : (k == 1 ? Y - p->H : Z - p->W);
+      if (starts[n * 3 + k] < 0 || starts[n * 3 + k] > lim) { seunet_set_error("forward_window: window %d out of bounds", n); return 1; }
+    }
+  WindowSink sink{acc, X, Y, Z, acc_log2, starts};
+  p->skip_head0 = true;
+  const int rc = forward_impl(p, x, xs, x_offsets, params, drop0, drop1, nullptr, nullptr, &sink, (cudaStream_t)stream);
+  p->skip_head0 = false;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256, C == 64 ? 3 : (C == 32 ? 4 : 6)) apply_ss
     *reinterpret_cast<float4*>(r) = *reinterpret_cast<const float4*>(sm + k * 8);
     *reinterpret_cast<float4*>(r + 4) = *reinterpret_cast<const float4*>(sm + k * 8 + 4);
   };
+  const bool has_t = a.T != nullptr;     // window plans drop head 0: its blocks neither fold nor touch the accumulator
   float* tp0 = a.T + (size_t)n * a.V;
   const float wcst = a.wcst[n];
 #pragma unroll 1
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(256, C == 64 ? 3 : (C == 32 ? 4 : 6)) apply_ss
     const long long v = (blockIdx.x * (long long)VPT + u) * blockDim.x + threadIdx.x;
     if (v >= a.V) break;
     float* tp = tp0 + v;
-    const float t_old = a.t_init ? 0.f : *tp;   // issued with the raw loads, not after the gate arithmetic
+    const float t_old = (a.t_init || !has_t) ? 0.f : *tp;   // issued with the raw loads, not after the gate arithmetic
     float e[C];
     float g1 = 0.f;
     Chunk8 in[C / 8];
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(256, C == 64 ? 3 : (C == 32 ? 4 : 6)) apply_ss
 #pragma unroll
       for (int i = 0; i < 8; ++i) { e[k * 8 + i] *= g1; t = fmaf(weff[i], e[k * 8 + i], t); }
     }
-    *tp = t_old + t;
+    if (has_t) *tp = t_old + t;
     if (a.dest) {
 #pragma unroll
       for (int k = 0; k < C / 8; ++k)

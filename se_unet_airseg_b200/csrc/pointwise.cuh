@@ -24,7 +24,7 @@ struct SseArgs {
   long long V;
   const float* wse; const float* wse2;     // gate weights (C floats each), wse2 may be null (1 gate)
   const float* weff; const float* wcst;    // folded side-branch/head weights [n][C], [n]
-  float* T; int t_init;                    // head accumulator [n][V]
+  float* T; int t_init;                    // head accumulator [n][V]; null = this block's head is not wanted (window plans: head 0)
   act_t* dest; int dest_chunks; int dest_off;  // gated activations, may be null
 };
 int launch_apply_sse(int C, int N, const SseArgs& a, cudaStream_t st);
@@ -70,5 +70,8 @@ struct HeadArgs {
   const float* T1[3];             // head 1 accumulators at S, S/2, S/4
   const float* bias0; const float* bias1;
   float* pred0; float* pred1;     // [n][1][D][H][W] contiguous fp32
+  // window sink (seunet_forward_window): head 0 is skipped and sigmoid(pred1) of sample n is added, in fixed point, to the
+  // (X,Y,Z) accumulator volume at origin s[n] (prediction.py:103-106) instead of being stored
+  unsigned int* acc; int X, Y, Z; float acc_scale; int s[kMaxWindowBatch][3];
 };
 int launch_head(const HeadArgs& a, cudaStream_t st);

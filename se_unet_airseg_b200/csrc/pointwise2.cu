@@ -172,6 +172,10 @@ constexpr int kHeadLines = 8;
 // along d and h (block-/line-uniform weights, 4 coalesced loads per coarse element) into shared memory; phase 2 is the w
 // lerp from shared memory: 2 LDS + 2 FMA per (voxel, level, head) instead of 8 gathers + 7 lerps.  Issue-bound: the
 // interpolation parameters come from shared-memory tables (per-element recomputation measured 40 % slower).
+// SINK (sliding-window plans): only head 1 (prediction.py:103 drops p0), and instead of storing the logits the block adds
+// sigmoid(pred1) in fixed point to the volume accumulator - same arithmetic as window_accumulate_kernel (window.cu), so the
+// fused and the two-kernel paths agree bit for bit.
+template <bool SINK>
 __global__ void __launch_bounds__(256) head_tile_kernel(const __grid_constant__ HeadArgs a) {
   extern __shared__ float s_head[];   // lines: [level 1..3][head][line][W >> l]; then w tables [level][W]{i0 | i1<<16, l1}
   __shared__ __align__(16) int s_hoff[3][kHeadLines][4];
@@ -209,13 +213,15 @@ __global__ void __launch_bounds__(256) head_tile_kernel(const __grid_constant__ 
   for (int l = 1; l < 4; ++l) {
     const int Ws = W >> l;
     const size_t Vs = (size_t)(d.D >> l) * (d.H >> l) * Ws;
-    const float* t0 = a.T0[l] + (size_t)n * Vs;
+    if (SINK && l == 3) break;
+    const float* t0 = SINK ? nullptr : a.T0[l] + (size_t)n * Vs;
     const float* t1 = l < 3 ? a.T1[l] + (size_t)n * Vs : nullptr;
     const int4 o = *reinterpret_cast<const int4*>(s_hoff[l - 1][line]);
     const float4 q = *reinterpret_cast<const float4*>(s_hw[l - 1][line]);
     for (int w = lane; w < Ws; w += 32) {
-      s_head[base[l][0] + line * Ws + w] =
-          q.x * __ldg(t0 + o.x + w) + q.y * __ldg(t0 + o.y + w) + q.z * __ldg(t0 + o.z + w) + q.w * __ldg(t0 + o.w + w);
+      if (!SINK)
+        s_head[base[l][0] + line * Ws + w] =
+            q.x * __ldg(t0 + o.x + w) + q.y * __ldg(t0 + o.y + w) + q.z * __ldg(t0 + o.z + w) + q.w * __ldg(t0 + o.w + w);
       if (l < 3)
         s_head[base[l][1] + line * Ws + w] =
             q.x * __ldg(t1 + o.x + w) + q.y * __ldg(t1 + o.y + w) + q.z * __ldg(t1 + o.z + w) + q.w * __ldg(t1 + o.w + w);
@@ -228,26 +234,36 @@ __global__ void __launch_bounds__(256) head_tile_kernel(const __grid_constant__ 
   const int hy = hy0 + line;
   if (hy >= d.H) return;
   const size_t row = (size_t)n * V + ((size_t)dz * d.H + hy) * d.W;
+  unsigned int* accp = SINK ? a.acc + ((size_t)(a.s[n][0] + dz) * a.Y + (a.s[n][1] + hy)) * a.Z + a.s[n][2] : nullptr;
   for (int wx = lane; wx < W; wx += 32) {
-    float p0 = b0 + __ldg(a.T0[0] + row + wx);
+    float p0 = SINK ? 0.f : b0 + __ldg(a.T0[0] + row + wx);
     float p1 = b1 + __ldg(a.T1[0] + row + wx);
 #pragma unroll
     for (int l = 1; l < 4; ++l) {
+      if (SINK && l == 3) break;
       const int Ws = W >> l;
       const int2 tw = s_wtab[(l - 1) * W + wx];
       const int i0 = tw.x & 0xffff, i1 = tw.x >> 16;
       const float l1 = __int_as_float(tw.y);
-      const float* s0 = s_head + base[l][0] + line * Ws;
-      const float v0 = s0[i0];
-      p0 += fmaf(l1, s0[i1] - v0, v0);
+      if (!SINK) {
+        const float* s0 = s_head + base[l][0] + line * Ws;
+        const float v0 = s0[i0];
+        p0 += fmaf(l1, s0[i1] - v0, v0);
+      }
       if (l < 3) {
         const float* s1 = s_head + base[l][1] + line * Ws;
         const float u0 = s1[i0];
         p1 += fmaf(l1, s1[i1] - u0, u0);
       }
     }
-    a.pred0[row + wx] = p0;
-    a.pred1[row + wx] = p1;
+    if (SINK) {
+      float pr = 1.f / (1.f + expf(-p1));
+      pr = fminf(fmaxf(pr, 0.f), 1.f);
+      atomicAdd(accp + wx, __float2uint_rn(pr * a.acc_scale));
+    } else {
+      a.pred0[row + wx] = p0;
+      a.pred1[row + wx] = p1;
+    }
   }
 }
 
@@ -257,7 +273,8 @@ int launch_head(const HeadArgs& a, cudaStream_t st) {
   size_t floats = 0;
   for (int l = 1; l < 4; ++l) floats += (size_t)kHeadLines * (a.d.W >> l) * (l < 3 ? 2 : 1);
   const size_t smem = floats * sizeof(float) + (size_t)3 * a.d.W * sizeof(int2);
-  head_tile_kernel<<<grid, 256, smem, st>>>(a);
+  if (a.acc) head_tile_kernel<true><<<grid, 256, smem, st>>>(a);
+  else head_tile_kernel<false><<<grid, 256, smem, st>>>(a);
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(256, C == 64 ? 1 : 2) apply_sse_cat_kernel(con
   uint8_t* out_p = reinterpret_cast<uint8_t*>(f.out) + (size_t)n * f.out_chunks * plane_bytes + (warp * 32 + (lane >> 2)) * 16 + (lane & 3) * 4;
   float* Tn = a.T + (size_t)n * a.V + tid;
   const float wcst = a.wcst[n];
-  const bool t_init = a.t_init;
+  const bool has_t = a.T != nullptr;               // window plans drop head 0 (ec3): no accumulator traffic at all
+  const bool t_init = a.t_init || !has_t;
   // the block's tile sequence: whole groups g = blockIdx.x, + gridDim.x, ...; `cur` is consumed, `pf` runs STAGES tiles ahead
   struct TileIt { long long g; int ts; };
   auto tile_of = [&](const TileIt& it) { return it.g * kCatTileGroup + it.ts; };
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(256, C == 64 ? 1 : 2) apply_sse_cat_kernel(con
         for (int i = 0; i < 8; ++i) { e[k * 8 + i] *= g1; t = fmaf(weff[i], e[k * 8 + i], t); }
         st_chunk(rowp + k * 16, floats_to_chunk(e + k * 8));   // same rounding as the stored concat slice
       }
-      Tn[t256] = t_old + t;
+      if (has_t) Tn[t256] = t_old + t;
     } else {
 #pragma unroll
       for (int k = 0; k < NCH; ++k) st_chunk(rowp + k * 16, Chunk8{{0u, 0u, 0u, 0u}});   // zero rows: zero outputs, nothing added to the statistics

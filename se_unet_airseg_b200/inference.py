@@ -67,10 +67,14 @@ def coverage_counts(length, starts, cube):
 class SlidingWindowPredictor:
     """Runs `model` (se_unet_airseg_b200.SE_UNet on a CUDA device, eval mode like prediction.py:64) over a CT volume."""
 
-    def __init__(self, model, cube=128, step=64, batch=7, threshold=0.5, streams=3):
+    def __init__(self, model, cube=128, step=64, batch=7, threshold=0.5, streams=3, fuse_head=True):
         """streams > 1: consecutive window batches run on different CUDA streams with their own plan workspaces, so the
-        HBM-bound passes of one batch overlap the tensor-bound convolutions of the other (both fit on an SM together)."""
+        HBM-bound passes of one batch overlap the tensor-bound convolutions of the other (both fit on an SM together).
+        fuse_head: one `seunet_forward_window` call per batch - prediction.py:103 discards the first output p0, so its whole
+        head is not computed, and sigmoid(p) goes from the head kernel straight into the accumulator volume.  False: the
+        two-call path (seunet_forward, seunet_window_accumulate); both give bit-identical volumes."""
         self.model = model
+        self.fuse_head = fuse_head
         self.cube, self.step, self.batch, self.threshold = cube, step, batch, threshold
         self.nstreams = max(1, streams)
         self._streams = None
@@ -158,11 +162,16 @@ class SlidingWindowPredictor:
                 ones0, ones1, pred0, pred1 = self._buffers(plan, b, dev)
                 offs = (ctypes.c_int64 * b)(*[w[0] * sD + w[1] * sH + w[2] * sW for w in wins[i:i + b]])
                 strides = (ctypes.c_int64 * 5)(0, sC, sD, sH, sW)
-                _lib.check(L.seunet_forward(plan.handle, _lib.ptr(x2), strides, offs, _lib.ptr(flat), _lib.ptr(ones0),
-                                            _lib.ptr(ones1), _lib.ptr(pred0), _lib.ptr(pred1), stp), "seunet_forward")
                 starts = (ctypes.c_int * (3 * b))(*[v for w in wins[i:i + b] for v in w])
-                _lib.check(L.seunet_window_accumulate(_lib.ptr(pred1), starts, b, cube, cube, cube, _lib.ptr(g["acc"]),
-                                                      X, Y, Z, 1, g["acc_log2"], stp), "seunet_window_accumulate")
+                if self.fuse_head:
+                    _lib.check(L.seunet_forward_window(plan.handle, _lib.ptr(x2), strides, offs, _lib.ptr(flat), _lib.ptr(ones0),
+                                                       _lib.ptr(ones1), starts, _lib.ptr(g["acc"]), X, Y, Z, g["acc_log2"], stp),
+                               "seunet_forward_window")
+                else:
+                    _lib.check(L.seunet_forward(plan.handle, _lib.ptr(x2), strides, offs, _lib.ptr(flat), _lib.ptr(ones0),
+                                                _lib.ptr(ones1), _lib.ptr(pred0), _lib.ptr(pred1), stp), "seunet_forward")
+                    _lib.check(L.seunet_window_accumulate(_lib.ptr(pred1), starts, b, cube, cube, cube, _lib.ptr(g["acc"]),
+                                                          X, Y, Z, 1, g["acc_log2"], stp), "seunet_window_accumulate")
             i += b
         if self.nstreams > 1:
             for s_ in streams:

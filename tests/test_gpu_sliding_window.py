@@ -88,3 +88,23 @@ def test_full_size_volume_properties():
     _, prob2 = sw2.predict_device(img, return_prob=True)
     assert (prob2 - prob).abs().max().item() <= 1e-6
     assert (mask != (prob2 >= 0.5)).sum().item() <= 2
+
+
+@pytest.mark.parametrize("shape,cube,step,batch", [((40, 56, 48), 32, 16, 5), ((128, 192, 136), 128, 64, 2)])
+def test_fused_window_step_equals_forward_plus_accumulate(shape, cube, step, batch):
+    """seunet_forward_window (head 0 skipped - prediction.py:103 discards p0 -, sigmoid(p) added to the accumulator by the head
+    kernel) against the two-call path seunet_forward + seunet_window_accumulate: the same fixed-point volume, bit for bit."""
+    from se_unet_airseg_b200 import SE_UNet
+    from se_unet_airseg_b200.inference import SlidingWindowPredictor
+    sd = oracle.init_params(2, 1, seed=777)
+    m = SE_UNet(2, 1)
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    img = _synthetic_ct(shape, 3).cuda()
+    # one stream: the per-window forward is then a fixed function of the window (no cross-stream ordering of the statistics atomics)
+    fused = SlidingWindowPredictor(m, cube=cube, step=step, batch=batch, streams=1, fuse_head=True)
+    plain = SlidingWindowPredictor(m, cube=cube, step=step, batch=batch, streams=1, fuse_head=False)
+    mask_f, prob_f = fused.predict_device(img, return_prob=True)
+    mask_p, prob_p = plain.predict_device(img, return_prob=True)
+    assert torch.equal(prob_f, prob_p) and torch.equal(mask_f, mask_p)
+    assert 0.0 < prob_f.mean().item() < 1.0
