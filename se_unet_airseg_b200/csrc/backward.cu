@@ -245,7 +245,7 @@ int launch_norm_bwd_b(const NormBwdArgs& a, cudaStream_t st) {
 // =============================================================================================
 // CAT block backward, pass A:  out = lrelu(IN(y)) [+ lrelu(IN(Wx x))], optional 2x2x2 max-pool fan-out
 // =============================================================================================
-struct CatCoef { float mean[8], rstd[8], mx[8], rx[8], w0[8], w1[8]; };
+struct __align__(16) CatCoef { float mean[8], rstd[8], mx[8], rx[8], w0[8], w1[8]; };
 
 __device__ __forceinline__ void cat_prologue(const act_t*, const double* stats, int stats_c, long long V, int n, int k, bool hasx,
                                              const float* wx, int in_ch, const double* mom, CatCoef* s) {
@@ -339,56 +339,82 @@ __global__ void __launch_bounds__(256, 2) cat_bwd_a_kernel(const __grid_constant
         accumulate(v, ny, nx, G);
       }
   } else {
-    // POOL: a thread owns the 2 (d) x 2 (h) voxels of a pooling window at ONE w; the w pair (adjacent lanes, W is even)
-    // settles the arg-max with one shuffle.  Scan index inside the window: J = 4*dd + 2*dh + dw (max_pool3d keeps the first
-    // maximum in (d,h,w) order).
+    // POOL: a thread owns the 2 (h) voxels of a pooling window at ONE (d, w); the four lanes l, l^1 (w pair; W is even) and
+    // l^16 (d pair) settle the window's arg-max with two shuffle rounds.  Scan index inside the window: J = 4*dd + 2*dh + dw
+    // (max_pool3d keeps the first maximum in (d,h,w) order).
+    // Round 2: every load of the thread is issued up front - the two raw chunks stay packed in registers for both passes, the
+    // x values and the pooled gradient ride along, the second output gradient is fetched while the first is processed.  (The
+    // first version walked a 2x2 (d,h) window twice with one load in flight per thread: ncu 2.4 TB/s, 58 % of the stall
+    // samples on that load; with all four voxels unrolled in one thread the x-branch instance spilled 500 bytes.)
     const int Dp = a.d.D >> 1, Hp = H >> 1, Wp = W >> 1;
     const long long Vp = (long long)Dp * Hp * Wp;
     const grad_t* gpool = a.gp + ((size_t)n * a.gp_chunks + a.gp_off + k) * Vp * 8;
-    const int per_plane = Hp * W, rounded = (per_plane + 31) & ~31;
+    const int per_plane = Hp * W, groups = (per_plane + 15) >> 4;
     for (int pd = blockIdx.x; pd < Dp; pd += gridDim.x)
-      for (int t = threadIdx.x; t < rounded; t += blockDim.x) {
-        const bool live = t < per_plane;
-        const int tt = live ? t : 0;
-        const int ph = tt / W, wx = tt - ph * W;
-        float best[8];
-        int arg[8];
+      for (int t = threadIdx.x; t < groups * 32; t += blockDim.x) {
+        const int l = t & 31, dd = l >> 4, idx = (t >> 5) * 16 + (l & 15);
+        const bool live = idx < per_plane;
+        const int ii = live ? idx : 0;
+        const int ph = ii / W, wx = ii - ph * W, dz = pd * 2 + dd;
+        Chunk8 rc[2];
+        float xa[2], xb[2];
+        long long vj[2];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; arg[i] = 0; }
-#pragma unroll 1   // (fully unrolled, the two window passes need 252 registers: one block per SM)
-        for (int j = 0; j < 4; ++j) {
-          const int dz = pd * 2 + (j >> 1), hy = ph * 2 + (j & 1);
-          const long long v = ((long long)dz * H + hy) * W + wx;
+        for (int j = 0; j < 2; ++j) {
+          const int hy = ph * 2 + j;
+          vj[j] = ((long long)dz * H + hy) * W + wx;
+          rc[j] = ld_chunk(rawp + (size_t)vj[j] * 8);
+          xvals(dz, hy, wx, xa[j], xb[j]);
+        }
+        float GP[8], Gn[8];
+        ld_grad8_cached(gpool + (size_t)(((long long)pd * Hp + ph) * Wp + (wx >> 1)) * 8, GP);   // the four lanes of a window read the same chunk
+        ld_grad8(gp_ + (size_t)vj[0] * 8, Gn);
+        auto norms_r = [&](int j, float* ny, float* nx) {
+          float f[8];
+          chunk_to_floats(rc[j], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            ny[i] = (f[i] - s.mean[i]) * s.rstd[i];
+            nx[i] = HASX ? (fmaf(s.w0[i], xa[j], s.w1[i] * xb[j]) - s.mx[i]) * s.rx[i] : 0.f;
+          }
+        };
+        float best[8];
+        unsigned argp = 0;     // 4 bits per channel: scan index J of the running maximum
+#pragma unroll
+        for (int i = 0; i < 8; ++i) best[i] = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
           float ny[8], nx[8];
-          norms(v, dz, hy, wx, ny, nx);
-          const int J = (j >> 1) * 4 + (j & 1) * 2 + (wx & 1);
+          norms_r(j, ny, nx);
+          const unsigned J = (unsigned)(dd * 4 + j * 2 + (wx & 1));
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float o = lrelu_(ny[i]) + (HASX ? lrelu_(nx[i]) : 0.f);
-            if (o > best[i]) { best[i] = o; arg[i] = J; }
+            if (o > best[i]) { best[i] = o; argp = (argp & ~(0xFu << (4 * i))) | (J << (4 * i)); }
           }
         }
-        float GP[8];
-        ld_grad8(gpool + (size_t)(((long long)pd * Hp + ph) * Wp + (wx >> 1)) * 8, GP);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float ob = __shfl_xor_sync(0xffffffffu, best[i], 1);
-          const int oa = __shfl_xor_sync(0xffffffffu, arg[i], 1);
-          const bool mine = best[i] > ob || (best[i] == ob && arg[i] < oa);
-          if (!mine) arg[i] = -1;   // the partner lane owns the maximum of this channel
+        for (int m = 1; m <= 16; m <<= 4) {           // partner along w, then partner along d
+          const unsigned oap = __shfl_xor_sync(0xffffffffu, argp, m);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best[i], m);
+            const unsigned ma = (argp >> (4 * i)) & 0xFu, oa = (oap >> (4 * i)) & 0xFu;
+            if (ob > best[i] || (ob == best[i] && oa < ma)) { best[i] = ob; argp = (argp & ~(0xFu << (4 * i))) | (oa << (4 * i)); }
+          }
         }
         if (!live) continue;
-#pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          const int dz = pd * 2 + (j >> 1), hy = ph * 2 + (j & 1);
-          const long long v = ((long long)dz * H + hy) * W + wx;
-          const int J = (j >> 1) * 4 + (j & 1) * 2 + (wx & 1);
-          float ny[8], nx[8], G[8];
-          norms(v, dz, hy, wx, ny, nx);
-          ld_grad8(gp_ + (size_t)v * 8, G);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) G[i] += (arg[i] == J) ? GP[i] : 0.f;
-          accumulate(v, ny, nx, G);
+        for (int j = 0; j < 2; ++j) {
+          const unsigned J = (unsigned)(dd * 4 + j * 2 + (wx & 1));
+          float ny[8], nx[8], G[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) G[i] = Gn[i];
+          if (j == 0) ld_grad8(gp_ + (size_t)vj[1] * 8, Gn);
+          norms_r(j, ny, nx);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) G[i] += (((argp >> (4 * i)) & 0xFu) == J) ? GP[i] : 0.f;
+          accumulate(vj[j], ny, nx, G);
         }
       }
   }
