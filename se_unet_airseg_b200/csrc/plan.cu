@@ -170,6 +170,12 @@ struct seunet_plan {
   uint8_t* ws = nullptr;
   uint8_t* wimg = nullptr;
   XOffsets xo;                      // per-sample input offsets of the current forward
+  // backward concurrency (plan_bwd.inc): plan-owned side streams forked from / joined to the caller's stream with events.
+  // side[0] carries the weight gradients, side[1..3] the extra dgrad pieces of layers wider than 64 channels.
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_side[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool wg_pending = false;          // a wgrad on side[0] has not been joined to the caller's stream yet
+  long long conc_vox = 0;           // layers with batch * voxels <= conc_vox use the side streams (0: never)
   // optional per-launch CUDA-event timing (bench roofline); events live on the caller's stream
   bool timing = false;
   std::vector<cudaEvent_t> ev;
@@ -321,6 +327,11 @@ extern "C" int seunet_plan_create(seunet_plan_t** out, int batch, int D, int H, 
 extern "C" void seunet_plan_destroy(seunet_plan_t* p) {
   if (!p) return;
   for (auto e : p->ev) cudaEventDestroy(e);
+  for (int i = 0; i < 4; ++i) {
+    if (p->ev_side[i]) cudaEventDestroy(p->ev_side[i]);
+    if (p->side[i]) cudaStreamDestroy(p->side[i]);
+  }
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   delete p;
 }
 extern "C" int seunet_plan_set_timing(seunet_plan_t* p, int on) { if (!p) return 1; p->timing = on != 0; p->ev_n = 0; return 0; }
