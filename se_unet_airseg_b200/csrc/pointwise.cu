@@ -4,6 +4,8 @@
 // warp touches 512 contiguous bytes per chunk plane.
 #include "pointwise.cuh"
 #include <cstring>
+#include <cstdlib>
+#include <cstdint>
 
 constexpr float kInEps = 1e-5f;   // nn.InstanceNorm3d default eps (SE_UNet.py:17,43,59)
 
@@ -88,11 +90,134 @@ __global__ void __launch_bounds__(128) input_prep_kernel(const float* __restrict
   }
 }
 
+// Round 2, contiguous inputs (last-axis stride 1, 16-byte aligned rows - every caller in this repo): a lane owns 4 consecutive
+// w voxels of one h row and walks the 4 d-planes of a 4x4x4 block row; a warp is 4 (h) x 8 (w quads), so every load is a
+// coalesced 128-bit vector per channel, every lane stores 64 contiguous bytes of chunks, the w pairs of the pooling windows
+// stay inside the thread and the h pairs / quads are two shuffles.  (ncu on the one-thread-per-4x4x4-block version above:
+// 47 % of the DRAM peak; its scalar loads are 16 B apart between lanes and its chunk stores 64 B apart.)
+constexpr int kPrepDG = 4;   // 4x4x4 block rows along d per warp (amortises the moment reduction)
+__global__ void __launch_bounds__(128) input_prep_vec_kernel(const float* __restrict__ x, long long sN, long long sC, long long sD,
+                                                             long long sH, const __grid_constant__ XOffsets xo, int in_ch, Dims d,
+                                                             act_t* __restrict__ xb, float* __restrict__ xp1,
+                                                             float* __restrict__ xp2, double* __restrict__ mom) {
+  const int n = blockIdx.y;
+  const long long xbase = xo.use ? xo.off[n] : n * sN;
+  const int D4 = d.D >> 2, H4 = d.H >> 2, W4 = d.W >> 2;
+  const int segs = (d.W + 31) >> 5, dgs = (D4 + kPrepDG - 1) / kPrepDG;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gw = (long long)blockIdx.x * 4 + warp;
+  float m[3][5];
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+#pragma unroll
+    for (int i = 0; i < 5; ++i) m[l][i] = 0.f;
+  if (gw < (long long)segs * H4 * dgs) {
+    const int seg = (int)(gw % segs), bh = (int)((gw / segs) % H4), bdg = (int)(gw / ((long long)segs * H4));
+    const int hq = lane >> 3, wq = lane & 7;
+    const int w0 = seg * 32 + wq * 4, hy = bh * 4 + hq;
+    const bool act = w0 < d.W;
+    const int H2 = d.H >> 1, W2 = d.W >> 1;
+    for (int bd = bdg * kPrepDG; bd < min(D4, bdg * kPrepDG + kPrepDG); ++bd) {
+      float p2[kMaxInCh], q01[kMaxInCh], q23[kMaxInCh];
+#pragma unroll
+      for (int c = 0; c < kMaxInCh; ++c) p2[c] = q01[c] = q23[c] = -INFINITY;
+#pragma unroll
+      for (int dd = 0; dd < 4; ++dd) {
+        const int dz = bd * 4 + dd;
+        float4 v[kMaxInCh];
+#pragma unroll
+        for (int c = 0; c < kMaxInCh; ++c) {
+          v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (act && c < in_ch) v[c] = __ldg(reinterpret_cast<const float4*>(x + xbase + c * sC + dz * sD + hy * sH + w0));
+        }
+        if (act) {
+          act_t* op = xb + ((((size_t)n * d.D + dz) * d.H + hy) * (size_t)d.W + w0) * 8;
+          const float* v0 = reinterpret_cast<const float*>(&v[0]);
+          const float* v1 = reinterpret_cast<const float*>(&v[kMaxInCh - 1]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            f[0] = v0[j];
+            if (kMaxInCh > 1) f[1] = v1[j];
+            st_chunk(op + j * 8, floats_to_chunk(f));
+            const float a0 = v0[j], a1 = kMaxInCh > 1 ? v1[j] : 0.f;
+            m[0][0] += a0; m[0][1] += a1; m[0][2] += a0 * a0; m[0][3] += a1 * a1; m[0][4] += a0 * a1;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < kMaxInCh; ++c) {
+          const float a = act ? fmaxf(v[c].x, v[c].y) : -INFINITY, b = act ? fmaxf(v[c].z, v[c].w) : -INFINITY;
+          q01[c] = (dd & 1) ? fmaxf(q01[c], a) : a;
+          q23[c] = (dd & 1) ? fmaxf(q23[c], b) : b;
+        }
+        if (dd & 1) {   // a 2x2x2 window is complete along d: finish it along h
+          float r01[kMaxInCh], r23[kMaxInCh];
+#pragma unroll
+          for (int c = 0; c < kMaxInCh; ++c) {
+            r01[c] = fmaxf(q01[c], __shfl_xor_sync(0xffffffffu, q01[c], 8));
+            r23[c] = fmaxf(q23[c], __shfl_xor_sync(0xffffffffu, q23[c], 8));
+            p2[c] = fmaxf(p2[c], fmaxf(r01[c], r23[c]));
+          }
+          if (act && !(hq & 1)) {
+            const int d1 = dz >> 1, h1 = hy >> 1, w1 = w0 >> 1;
+            float pa[2] = {0.f, 0.f}, pb[2] = {0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < kMaxInCh; ++c)
+              if (c < in_ch) {
+                pa[c] = r01[c]; pb[c] = r23[c];
+                *reinterpret_cast<float2*>(xp1 + (((size_t)n * in_ch + c) * (d.D >> 1) + d1) * (size_t)H2 * W2 + (size_t)h1 * W2 + w1) =
+                    make_float2(r01[c], r23[c]);
+              }
+            m[1][0] += pa[0] + pb[0]; m[1][1] += pa[1] + pb[1]; m[1][2] += pa[0] * pa[0] + pb[0] * pb[0];
+            m[1][3] += pa[1] * pa[1] + pb[1] * pb[1]; m[1][4] += pa[0] * pa[1] + pb[0] * pb[1];
+          }
+        }
+      }
+      float t2[2] = {0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < kMaxInCh; ++c) {
+        p2[c] = fmaxf(p2[c], __shfl_xor_sync(0xffffffffu, p2[c], 16));
+        if (act && hq == 0 && c < in_ch) {
+          t2[c] = p2[c];
+          xp2[(((size_t)n * in_ch + c) * D4 + bd) * (size_t)H4 * W4 + (size_t)bh * W4 + (w0 >> 2)] = p2[c];
+        }
+      }
+      if (act && hq == 0) { m[2][0] += t2[0]; m[2][1] += t2[1]; m[2][2] += t2[0] * t2[0]; m[2][3] += t2[1] * t2[1]; m[2][4] += t2[0] * t2[1]; }
+    }
+  }
+  __shared__ double red[4][15];
+#pragma unroll
+  for (int l = 0; l < 3; ++l)
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const double s = warp_sum_d((double)m[l][i]);
+      if (lane == 0) red[warp][l * 5 + i] = s;
+    }
+  __syncthreads();
+  if (threadIdx.x < 15) {
+    const double s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    const int l = threadIdx.x / 5, i = threadIdx.x % 5;
+    atomicAdd(mom + ((size_t)l * gridDim.y + n) * kMomStride + i, s);
+  }
+}
+
 int launch_input_prep(const float* x, const long long* xs, const XOffsets& xo, int in_ch, Dims d, act_t* xb, float* xp1, float* xp2,
                       double* mom, cudaStream_t st) {
   if (in_ch < 1 || in_ch > kMaxInCh) { seunet_set_error("in_channel %d unsupported (1..%d)", in_ch, kMaxInCh); return 1; }
   if ((d.D | d.H | d.W) & 7) { seunet_set_error("spatial dims must be multiples of 8"); return 1; }
   SEUNET_CUDA_CHECK(cudaMemsetAsync(mom, 0, sizeof(double) * 3 * d.N * kMomStride, st));
+  // vector path: contiguous last axis and 16-byte aligned rows
+  bool vec = xs[4] == 1 && ((uintptr_t)x & 15) == 0 && ((xs[0] | xs[1] | xs[2] | xs[3]) & 3) == 0;
+  if (xo.use)
+    for (int n = 0; n < d.N && n < kMaxWindowBatch; ++n) vec = vec && (xo.off[n] & 3) == 0;
+  static const bool allow_vec = !(getenv("SEUNET_PREP_VEC") && atoi(getenv("SEUNET_PREP_VEC")) == 0);
+  if (vec && allow_vec) {
+    const long long warps = (long long)((d.W + 31) / 32) * (d.H / 4) * ((d.D / 4 + kPrepDG - 1) / kPrepDG);
+    dim3 gridv((unsigned)((warps + 3) / 4), d.N);
+    input_prep_vec_kernel<<<gridv, 128, 0, st>>>(x, xs[0], xs[1], xs[2], xs[3], xo, in_ch, d, xb, xp1, xp2, mom);
+    SEUNET_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   const long long nb = (long long)(d.D / 4) * (d.H / 4) * (d.W / 4);
   dim3 grid((unsigned)((nb + 127) / 128), d.N);
   input_prep_kernel<<<grid, 128, 0, st>>>(x, xs[0], xs[1], xs[2], xs[3], xs[4], xo, in_ch, d, xb, xp1, xp2, mom);
