@@ -234,11 +234,19 @@ int launch_input_prep(const float* x, const long long* xs, const XOffsets& xo, i
 // VPT voxels per thread (round 2): ncu on the 8- and 16-channel instances showed 60-70 % issue-slot utilisation at 46 % of the DRAM
 // peak - with one 16/32-byte voxel per thread the per-block prologue (fp64 statistics, barrier) and the address arithmetic
 // outweigh the payload; those instances now loop over 4 voxels per thread (rolled: hoisting the loads of several voxels spilled).
+constexpr int kSseSplitDefault = 1;
 template <int C> struct SseVpt { static constexpr int value = C <= 16 ? 4 : 1; };
 
-template <int C, int GATES>
-__global__ void __launch_bounds__(256, C == 64 ? 3 : (C == 32 ? 4 : 6)) apply_sse_kernel(const __grid_constant__ SseArgs a) {
+// SPLIT = 2 (round 2, the 64-channel instances): the two lanes l and l^16 of a warp share a voxel, 32 channels each - half the
+// registers (four resident blocks instead of three, no spill), half the serial arithmetic per thread and twice the threads
+// on the 32^3 / 16^3 levels, where the one-thread-per-voxel version was latency-bound (ncu: 19 us for 59 MB, 34 % of the
+// warp slots).  The gate sums and the folded side-branch sum are completed with one shuffle each.
+template <int C, int GATES, int SPLIT>
+__global__ void __launch_bounds__(256, SPLIT == 2 ? 4 : (C == 64 ? 3 : (C == 32 ? 4 : 6))) apply_sse_kernel(const __grid_constant__ SseArgs a) {
   constexpr int VPT = SseVpt<C>::value;
+  constexpr int KPT = C / 8 / SPLIT;       // channel chunks per thread
+  constexpr int CT = C / SPLIT;            // channels per thread
+  static_assert(SPLIT == 1 || VPT == 1, "split variant: one voxel per thread pair");
   __shared__ __align__(16) float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -261,22 +269,27 @@ __global__ void __launch_bounds__(256, C == 64 ? 3 : (C == 32 ? 4 : 6)) apply_ss
   const bool has_t = a.T != nullptr;     // window plans drop head 0: its blocks neither fold nor touch the accumulator
   float* tp0 = a.T + (size_t)n * a.V;
   const float wcst = a.wcst[n];
+  // SPLIT == 2: lanes 0-15 hold chunks 0..KPT-1 of 16 consecutive voxels, lanes 16-31 chunks KPT..2*KPT-1 of the same voxels
+  const int sub = SPLIT == 2 ? (threadIdx.x >> 4) & 1 : 0;
+  const int tvox = SPLIT == 2 ? (threadIdx.x & 15) | ((threadIdx.x >> 5) << 4) : threadIdx.x;
+  constexpr int VPB = 256 / SPLIT;
+  const int k0 = sub * KPT;
 #pragma unroll 1
   for (int u = 0; u < VPT; ++u) {
-    const long long v = (blockIdx.x * (long long)VPT + u) * blockDim.x + threadIdx.x;
-    if (v >= a.V) break;
+    const long long v = (blockIdx.x * (long long)VPT + u) * VPB + tvox;
+    if (v >= a.V) break;                    // (V is a multiple of 32: both lanes of a pair leave together)
     float* tp = tp0 + v;
-    const float t_old = (a.t_init || !has_t) ? 0.f : *tp;   // issued with the raw loads, not after the gate arithmetic
-    float e[C];
+    const float t_old = (a.t_init || !has_t || sub) ? 0.f : *tp;   // issued with the raw loads, not after the gate arithmetic
+    float e[CT];
     float g1 = 0.f;
-    Chunk8 in[C / 8];
+    Chunk8 in[KPT];
 #pragma unroll
-    for (int k = 0; k < C / 8; ++k) in[k] = ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8);
+    for (int k = 0; k < KPT; ++k) in[k] = ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k0 + k) * a.V + v) * 8);
 #pragma unroll
-    for (int k = 0; k < C / 8; ++k) {
+    for (int k = 0; k < KPT; ++k) {
       float f[8], mean[8], rstd[8], wse[8];
       chunk_to_floats(in[k], f);
-      ld8(s_mean, k, mean); ld8(s_rstd, k, rstd); ld8(s_wse, k, wse);
+      ld8(s_mean, k0 + k, mean); ld8(s_rstd, k0 + k, rstd); ld8(s_wse, k0 + k, wse);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float t = lrelu_((f[i] - mean[i]) * rstd[i]);
@@ -284,41 +297,54 @@ __global__ void __launch_bounds__(256, C == 64 ? 3 : (C == 32 ? 4 : 6)) apply_ss
         g1 = fmaf(wse[i], t, g1);
       }
     }
+    if (SPLIT == 2) g1 += __shfl_xor_sync(0xffffffffu, g1, 16);
     g1 = sigmoidf_(g1);
     if (GATES == 2) {
       float g2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < C / 8; ++k) {
+      for (int k = 0; k < KPT; ++k) {
         float wse2[8];
-        ld8(s_wse2, k, wse2);
+        ld8(s_wse2, k0 + k, wse2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) { e[k * 8 + i] *= g1; g2 = fmaf(wse2[i], e[k * 8 + i], g2); }
       }
+      if (SPLIT == 2) g2 += __shfl_xor_sync(0xffffffffu, g2, 16);
       g1 = sigmoidf_(g2);   // the second gate multiplies below
     }
-    float t = wcst;
+    float t = sub ? 0.f : wcst;
 #pragma unroll
-    for (int k = 0; k < C / 8; ++k) {
+    for (int k = 0; k < KPT; ++k) {
       float weff[8];
-      ld8(s_weff, k, weff);
+      ld8(s_weff, k0 + k, weff);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { e[k * 8 + i] *= g1; t = fmaf(weff[i], e[k * 8 + i], t); }
     }
-    if (has_t) *tp = t_old + t;
+    if (SPLIT == 2) t += __shfl_xor_sync(0xffffffffu, t, 16);
+    if (has_t && !sub) *tp = t_old + t;
     if (a.dest) {
 #pragma unroll
-      for (int k = 0; k < C / 8; ++k)
-        st_chunk(a.dest + (((size_t)n * a.dest_chunks + a.dest_off + k) * a.V + v) * 8, floats_to_chunk(e + k * 8));
+      for (int k = 0; k < KPT; ++k)
+        st_chunk(a.dest + (((size_t)n * a.dest_chunks + a.dest_off + k0 + k) * a.V + v) * 8, floats_to_chunk(e + k * 8));
     }
   }
 }
 
 template <int C>
 static int launch_apply_sse_c(int N, const SseArgs& a, cudaStream_t st) {
+  static const int split_mask = getenv("SEUNET_SSE_SPLIT") ? atoi(getenv("SEUNET_SSE_SPLIT")) : kSseSplitDefault;   // bit 0: C = 64, bit 1: C = 32
+  if constexpr (C >= 32) {
+    if (split_mask & (C == 64 ? 1 : 2)) {
+      dim3 grid((unsigned)((a.V + 127) / 128), N);
+      if (a.wse2) apply_sse_kernel<C, 2, 2><<<grid, 256, 0, st>>>(a);
+      else apply_sse_kernel<C, 1, 2><<<grid, 256, 0, st>>>(a);
+      SEUNET_CUDA_CHECK(cudaGetLastError());
+      return 0;
+    }
+  }
   constexpr int VPB = 256 * SseVpt<C>::value;
   dim3 grid((unsigned)((a.V + VPB - 1) / VPB), N);
-  if (a.wse2) apply_sse_kernel<C, 2><<<grid, 256, 0, st>>>(a);
-  else apply_sse_kernel<C, 1><<<grid, 256, 0, st>>>(a);
+  if (a.wse2) apply_sse_kernel<C, 2, 1><<<grid, 256, 0, st>>>(a);
+  else apply_sse_kernel<C, 1, 1><<<grid, 256, 0, st>>>(a);
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
