@@ -4,6 +4,7 @@
 #include "backward.cuh"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 constexpr float kInEps = 1e-5f;
 
@@ -13,7 +14,7 @@ __device__ __forceinline__ void atomic_max_pos(unsigned int* p, float v) { atomi
 // =============================================================================================
 // SSE block backward, pass A
 // =============================================================================================
-template <int C, int GATES>
+template <int C, int GATES, int PF>
 __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant__ SseBwdArgs a) {
   constexpr int LPV = C / 8;     // lanes cooperating on one voxel (one 8-channel chunk each)
   constexpr int VPW = 32 / LPV;  // voxels per warp
@@ -43,34 +44,30 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
     for (int o = 1; o < LPV; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   };
-  // Software pipeline: the loads of the NEXT voxel group are issued before the arithmetic of the current one.  The kernel
-  // runs at 25 % occupancy (106 registers), so the bytes in flight per warp decide the achieved bandwidth (ncu: stalled
-  // on long-scoreboard, 2.9 TB/s without the prefetch).
+  // Software pipeline: the loads of the next TWO voxel groups are in flight during the arithmetic of the current one.  The
+  // kernel runs at 25 % occupancy (two blocks per SM), so the bytes in flight per warp decide the achieved bandwidth (ncu:
+  // stalled on long-scoreboard, 2.9 TB/s without prefetch; with ONE group ahead 512 threads x 52 B = 26 KB per SM are in
+  // flight, which caps the read rate near 3 TB/s - the 64-channel instances sat at 2.1 TB/s, the 32-channel ones at 4.4).
   const long long vstep = (long long)gridDim.x * 8 * VPW;
   const act_t* rawp = a.raw + ((size_t)n * a.raw_chunks + k) * a.V * 8;
   const grad_t* de0p = a.dE0 ? a.dE0 + ((size_t)n * a.dE0_chunks + a.dE0_off + k) * a.V * 8 : nullptr;
   const float* dTp = a.dT + (size_t)n * a.V;
-  Chunk8 raw_n;
-  float de0_n[8], dT_n = 0.f;
-  auto prefetch = [&](long long v) {
-    raw_n = ld_chunk_stream(rawp + (size_t)v * 8);
-    dT_n = dTp[v];
-    if (de0p) ld_grad8(de0p + (size_t)v * 8, de0_n);
+  struct Pre { Chunk8 raw; float de0[8]; float dT; };
+  auto prefetch = [&](Pre& p, long long v) {
+    p.raw = ld_chunk_stream(rawp + (size_t)v * 8);
+    p.dT = dTp[v];
+    if (de0p) ld_grad8(de0p + (size_t)v * 8, p.de0);
     else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) de0_n[i] = 0.f;
+      for (int i = 0; i < 8; ++i) p.de0[i] = 0.f;
     }
   };
-  const long long vb0 = ((long long)blockIdx.x * 8 + warp) * VPW;
-  if (vb0 < a.V) prefetch(vb0 + vsub);
-  for (long long vb = vb0; vb < a.V; vb += vstep) {
-    const long long v = vb + vsub;   // V is a multiple of 32, so the whole warp is in range
+  auto process = [&](const Pre& p, long long v) {
     float f[8], nn[8], av[8], e0[8], de0[8];
-    chunk_to_floats(raw_n, f);
-    const float dT = dT_n;
+    chunk_to_floats(p.raw, f);
+    const float dT = p.dT;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) de0[i] = de0_n[i];
-    if (vb + vstep < a.V) prefetch(v + vstep);
+    for (int i = 0; i < 8; ++i) de0[i] = p.de0[i];
     float p1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -124,6 +121,20 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
     }
     if (k == 0) cst += dT;
     st_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
+  };
+  // V is a multiple of 32, so the whole warp is in range whenever its first voxel is
+  const long long vb0 = ((long long)blockIdx.x * 8 + warp) * VPW;
+  Pre pre[PF];
+#pragma unroll
+  for (int j = 0; j < PF; ++j)
+    if (vb0 + j * vstep < a.V) prefetch(pre[j], vb0 + j * vstep + vsub);
+#pragma unroll 1
+  for (long long vb = vb0; vb < a.V; vb += vstep) {
+    const Pre cur = pre[0];
+#pragma unroll
+    for (int j = 0; j + 1 < PF; ++j) pre[j] = pre[j + 1];   // (13 register moves per ~200-instruction body)
+    if (vb + PF * vstep < a.V) prefetch(pre[PF - 1], vb + PF * vstep + vsub);
+    process(cur, vb + vsub);
   }
   // reduce over the voxel sub-lanes of the warp, then over warps, then one atomic per value per block
   auto wreduce = [&](float v) {
@@ -162,6 +173,8 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
   }
 }
 
+template <int C> constexpr bool kSseBwdDeep = false;   // measured: depth 2 spills (128 registers) and is 10-30 % slower
+
 template <int C>
 static int launch_sse_bwd_a_c(const SseBwdArgs& a, cudaStream_t st) {
   constexpr int VPB = 8 * (32 / (C / 8));
@@ -172,8 +185,16 @@ static int launch_sse_bwd_a_c(const SseBwdArgs& a, cudaStream_t st) {
   const long long floor_blocks = (148 * 4 + a.N - 1) / a.N;
   const long long gx = std::min<long long>(need, std::max<long long>(floor_blocks, std::min<long long>(148 * 8, need / 16)));
   dim3 grid((unsigned)gx, a.N);
-  if (a.wse2) sse_bwd_a_kernel<C, 2><<<grid, 256, 0, st>>>(a);
-  else sse_bwd_a_kernel<C, 1><<<grid, 256, 0, st>>>(a);
+  // prefetch depth 2 only where the one-group-ahead version is short of bytes in flight (A/B, tools/r02_call50.sh)
+  static const int pf_env = getenv("SEUNET_BWDA_PF") ? atoi(getenv("SEUNET_BWDA_PF")) : 0;
+  const bool deep = pf_env ? pf_env == 2 : kSseBwdDeep<C>;
+  if (deep) {
+    if (a.wse2) sse_bwd_a_kernel<C, 2, 2><<<grid, 256, 0, st>>>(a);
+    else sse_bwd_a_kernel<C, 1, 2><<<grid, 256, 0, st>>>(a);
+  } else {
+    if (a.wse2) sse_bwd_a_kernel<C, 2, 1><<<grid, 256, 0, st>>>(a);
+    else sse_bwd_a_kernel<C, 1, 1><<<grid, 256, 0, st>>>(a);
+  }
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -460,6 +460,7 @@ static int run_sse(seunet_plan* p, int i, const float* params, cudaStream_t st) 
   a.wcst = (const float*)(p->ws + p->wcst_off) + (size_t)i * p->N;
   a.T = (s.head == 0 && p->skip_head0) ? nullptr : (float*)(p->ws + (s.head == 0 ? p->T0_off[s.level] : p->T1_off[s.level]));
   a.t_init = (s.k % 3 == 0 && s.head == 0) || (s.head == 1 && s.k % 2 == 0);
+  a.inference = p->mode == 0;
   if (fuse_cat(p, kSseFuse[i])) {
     // the block output never leaves the SM: apply + CAT 1x1x1 conv in one pass (the CAT conv launch is skipped in run_cat)
     const CatDesc& c = kCat[kSseFuse[i]];
@@ -536,7 +537,7 @@ static int forward_impl(seunet_plan_t* p, const float* x, const int64_t* xs, con
   long long xs_ll[5];
   for (int k = 0; k < 5; ++k) xs_ll[k] = xs[k];
   if (launch_input_prep(x, xs_ll, p->xo, p->in_ch, p->dims(0), act(B_XB), (float*)(p->ws + p->xp1_off),
-                        (float*)(p->ws + p->xp2_off), (double*)(p->ws + p->mom_off), st)) return 1;
+                        (float*)(p->ws + p->xp2_off), (double*)(p->ws + p->mom_off), st, p->mode == 0)) return 1;
   if (launch_headw(params, drop0, drop1, p->N, p->headw, (float*)(p->ws + p->weff_off), (float*)(p->ws + p->wcst_off), st)) return 1;
   p->mark("prep", st);
   // encoder, level 0 (SE_UNet.py:183-189)

@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(128) input_prep_vec_kernel(const float* __rest
 }
 
 int launch_input_prep(const float* x, const long long* xs, const XOffsets& xo, int in_ch, Dims d, act_t* xb, float* xp1, float* xp2,
-                      double* mom, cudaStream_t st) {
+                      double* mom, cudaStream_t st, bool inference) {
   if (in_ch < 1 || in_ch > kMaxInCh) { seunet_set_error("in_channel %d unsupported (1..%d)", in_ch, kMaxInCh); return 1; }
   if ((d.D | d.H | d.W) & 7) { seunet_set_error("spatial dims must be multiples of 8"); return 1; }
   SEUNET_CUDA_CHECK(cudaMemsetAsync(mom, 0, sizeof(double) * 3 * d.N * kMomStride, st));
@@ -211,7 +211,7 @@ int launch_input_prep(const float* x, const long long* xs, const XOffsets& xo, i
   if (xo.use)
     for (int n = 0; n < d.N && n < kMaxWindowBatch; ++n) vec = vec && (xo.off[n] & 3) == 0;
   static const bool allow_vec = !(getenv("SEUNET_PREP_VEC") && atoi(getenv("SEUNET_PREP_VEC")) == 0);
-  if (vec && allow_vec) {
+  if (vec && allow_vec && inference) {
     const long long warps = (long long)((d.W + 31) / 32) * (d.H / 4) * ((d.D / 4 + kPrepDG - 1) / kPrepDG);
     dim3 gridv((unsigned)((warps + 3) / 4), d.N);
     input_prep_vec_kernel<<<gridv, 128, 0, st>>>(x, xs[0], xs[1], xs[2], xs[3], xo, in_ch, d, xb, xp1, xp2, mom);
@@ -333,7 +333,7 @@ template <int C>
 static int launch_apply_sse_c(int N, const SseArgs& a, cudaStream_t st) {
   static const int split_mask = getenv("SEUNET_SSE_SPLIT") ? atoi(getenv("SEUNET_SSE_SPLIT")) : kSseSplitDefault;   // bit 0: C = 64, bit 1: C = 32
   if constexpr (C >= 32) {
-    if (split_mask & (C == 64 ? 1 : 2)) {
+    if (a.inference && (split_mask & (C == 64 ? 1 : 2))) {
       dim3 grid((unsigned)((a.V + 127) / 128), N);
       if (a.wse2) apply_sse_kernel<C, 2, 2><<<grid, 256, 0, st>>>(a);
       else apply_sse_kernel<C, 1, 2><<<grid, 256, 0, st>>>(a);

@@ -16,7 +16,8 @@ __host__ __device__ inline long long dims_vox(const Dims& d) { return (long long
 // x (fp32, arbitrary strides) -> XB (storage type, 1 chunk plane, channels >= in_ch zero),
 // max-pooled fp32 copies at 1/2 and 1/4 resolution, and first/second moments at all three levels.
 int launch_input_prep(const float* x, const long long* xstride /*n,c,d,h,w in elements*/, const XOffsets& xo, int in_ch, Dims d,
-                      act_t* xb, float* xp1, float* xp2, double* mom /*[3][N][kMomStride]*/, cudaStream_t st);
+                      act_t* xb, float* xp1, float* xp2, double* mom /*[3][N][kMomStride]*/, cudaStream_t st,
+                      bool inference = false /* inference plans may use the vector kernel (different moment summation order) */);
 
 struct SseArgs {
   const act_t* raw; int raw_chunks;        // conv output [n][raw_chunks][V][8]
@@ -26,6 +27,8 @@ struct SseArgs {
   const float* weff; const float* wcst;    // folded side-branch/head weights [n][C], [n]
   float* T; int t_init;                    // head accumulator [n][V]; null = this block's head is not wanted (window plans: head 0)
   act_t* dest; int dest_chunks; int dest_off;  // gated activations, may be null
+  int inference;                           // inference plan: the two-lanes-per-voxel variant may be used (training plans keep the
+                                           // summation order the gradient parity bounds were measured with)
 };
 int launch_apply_sse(int C, int N, const SseArgs& a, cudaStream_t st);
 
