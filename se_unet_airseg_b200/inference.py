@@ -11,9 +11,10 @@ final mask crosses PCIe.
 
 Multi-GPU (BASELINE config 4): under torchrun the windows of ONE volume are sharded by patch -
 every rank takes a contiguous range of the window list (contiguous slabs along the first axis), accumulates
-into its own partial volume, and one NCCL integer SUM reduce over NVLink merges the partial volumes on rank 0
-(`predict_sharded` / `predict_device_sharded`).  Because the accumulation is integer, the N-rank mask is
-bit-identical to the 1-rank mask.
+into its own partial volume; the partial planes then go point-to-point (NCCL send/recv over NVLink/NVSwitch, all
+pairs at once) to the rank that owns them, every rank finalizes its 1/N of the planes and rank 0 collects the
+uint8 mask (`predict_sharded` / `predict_device_sharded`, `exchange_partials`).  Because the accumulation is
+integer, the N-rank mask is bit-identical to the 1-rank mask.
 """
 import ctypes
 
@@ -55,6 +56,64 @@ def shard_range(n, rank, world):
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def owner_ranges(length, world):
+    """Planes along the first axis that each rank FINALIZES in the sharded mode: an even contiguous partition."""
+    return [(length * q // world, length * (q + 1) // world) for q in range(world)]
+
+
+def _peer(group, q):
+    return dist.get_global_rank(group, q) if group is not None else q
+
+
+def exchange_partials(acc, slabs, owners, rank, world, group=None, staging=None):
+    """The exchange step of patch-sharded inference.  acc: this rank's partial fixed-point volume (X, Y, Z) int32, non-zero
+    only inside slabs[rank] = the planes its windows touched.  Every rank q owns the planes owners[q]; rank r sends q the
+    intersection of its slab with q's planes (contiguous memory: the first axis is the outermost) and adds what it receives
+    to its own planes - point-to-point over NVLink/NVSwitch, all pairs at once (one NCCL group).  On return
+    acc[owners[rank]] holds the sums over ALL ranks (integer adds: the result does not depend on the order); the rest of
+    acc is stale.  Compared with one SUM reduce of the whole volume to rank 0 this moves each partial plane once, to the
+    rank that needs it, instead of funnelling world x 420 MB through a reduction tree."""
+    x0, x1 = owners[rank]
+    ops, recvs = [], []
+    for q in range(world):
+        if q == rank:
+            continue
+        a, b = max(slabs[rank][0], owners[q][0]), min(slabs[rank][1], owners[q][1])
+        if a < b:
+            ops.append(dist.P2POp(dist.isend, acc[a:b], _peer(group, q), group))
+        a, b = max(slabs[q][0], x0), min(slabs[q][1], x1)
+        if a < b:
+            buf = staging.get((q, a, b)) if staging is not None else None
+            if buf is None:
+                buf = torch.empty_like(acc[a:b])
+                if staging is not None:
+                    staging[(q, a, b)] = buf
+            recvs.append((a, b, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, _peer(group, q), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    for a, b, buf in recvs:
+        acc[a:b] += buf
+
+
+def gather_planes(buf, owners, rank, world, group=None, root=0):
+    """Rank `root` receives buf[owners[q]] from every other rank q (straight into its own buf), the others send."""
+    ops = []
+    if rank == root:
+        for q in range(world):
+            a, b = owners[q]
+            if q != root and a < b:
+                ops.append(dist.P2POp(dist.irecv, buf[a:b], _peer(group, q), group))
+    else:
+        a, b = owners[rank]
+        if a < b:
+            ops.append(dist.P2POp(dist.isend, buf[a:b], _peer(group, root), group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
 
 
 def coverage_counts(length, starts, cube):
@@ -110,7 +169,8 @@ class SlidingWindowPredictor:
         _slab_events (internal, used by predict()): [(x_end, event)] - the two-HU-window input has already been produced slab
         by slab on a copy stream; a window batch waits only for the slabs it reads.
         _shard (internal, used by the *_sharded entry points): (rank, world, group) - run only this rank's range of the
-        window list and merge the partial volumes with one integer SUM reduce to rank 0; ranks != 0 return None."""
+        window list, exchange the partial planes with their owner ranks (exchange_partials), finalize the owned planes and
+        collect the mask on rank 0; ranks != 0 return None."""
         L = _lib.lib()
         m = self.model
         if m.in_channel != 2:
@@ -126,7 +186,16 @@ class SlidingWindowPredictor:
             img_dev = img_dev.contiguous()
             _lib.check(L.seunet_hu_windows(_lib.ptr(img_dev), dtype, X * Y * Z, float(hu_offset), _lib.ptr(g["x2"]), st),
                        "seunet_hu_windows")
-        g["acc"].zero_()
+        sharded = _shard is not None and _shard[1] > 1
+        if sharded:
+            rank, world, group = _shard
+            slabs = [self.shard_planes((X, Y, Z), r, world) for r in range(world)]
+            owners = owner_ranges(X, world)
+            own0, own1 = owners[rank]
+            z0, z1 = (min(slabs[rank][0], own0), max(slabs[rank][1], own1)) if slabs[rank][1] > slabs[rank][0] else (own0, own1)
+            g["acc"][z0:z1].zero_()          # only the planes this rank accumulates into or finalizes
+        else:
+            g["acc"].zero_()
         x2 = g["x2"]
         sN, sC, sD, sH, sW = x2.stride()
         cube = self.cube
@@ -178,12 +247,29 @@ class SlidingWindowPredictor:
                 done = torch.cuda.Event()
                 done.record(s_)
                 main.wait_event(done)
-        if _shard is not None and _shard[1] > 1:
-            # the one exchange step of patch sharding: partial fixed-point volumes -> rank 0 (NCCL over NVLink/NVSwitch)
-            dist.reduce(g["acc"], dst=dist.get_global_rank(_shard[2], 0) if _shard[2] is not None else 0,
-                        op=dist.ReduceOp.SUM, group=_shard[2])
-            if _shard[0] != 0:
+        if sharded:
+            # the exchange step of patch sharding (NCCL point-to-point over NVLink/NVSwitch): partial planes go to the rank
+            # that finalizes them; every rank divides / thresholds its own planes; rank 0 collects the uint8 mask planes
+            exchange_partials(g["acc"], slabs, owners, rank, world, group, g.setdefault("staging", {}))
+            key = ("counts_own", rank, world)
+            if key not in g:
+                cx = g["counts"][own0:own1]
+                g[key] = torch.cat([cx, g["counts"][X:]]).contiguous()
+            if own1 > own0:
+                plane = Y * Z
+                _lib.check(L.seunet_window_finalize(ctypes.c_void_p(g["acc"].data_ptr() + own0 * plane * 4), _lib.ptr(g[key]),
+                                                    own1 - own0, Y, Z, float(self.threshold),
+                                                    ctypes.c_void_p(g["mask"].data_ptr() + own0 * plane),
+                                                    1 if return_prob else 0, g["acc_log2"], st), "seunet_window_finalize")
+            gather_planes(g["mask"], owners, rank, world, group)
+            if return_prob:
+                gather_planes(g["acc"], owners, rank, world, group)      # fp32 means in the accumulator's 4-byte slots
+            if rank != 0:
                 return None
+            prob = g["acc"].view(torch.float32)
+            if reuse_output:
+                return (g["mask"], prob) if return_prob else g["mask"]
+            return (g["mask"].clone(), prob.clone()) if return_prob else g["mask"].clone()
         _lib.check(L.seunet_window_finalize(_lib.ptr(g["acc"]), _lib.ptr(g["counts"]), X, Y, Z, float(self.threshold),
                                             _lib.ptr(g["mask"]), 1 if return_prob else 0, g["acc_log2"], st),
                    "seunet_window_finalize")

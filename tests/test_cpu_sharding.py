@@ -1,16 +1,18 @@
 """CPU tests of the patch-sharded sliding-window driver's HOST logic (prediction.py:80-110 sharded by window):
-window partition, batch sizing, the planes each rank needs, and - world_size 2, gloo - that summing the ranks' fixed-point
-partial volumes with one integer reduce reproduces the single-process accumulation bit for bit."""
+window partition, batch sizing, the planes each rank needs, and - world_size 2 and 3, gloo - that the point-to-point
+exchange of the ranks' fixed-point partial planes (exchange_partials + gather_planes, the code predict_device runs over
+NCCL) reproduces the single-process accumulation bit for bit."""
 import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from se_unet_airseg_b200.inference import (SlidingWindowPredictor, coverage_counts, shard_range, split_batches,
-                                           window_starts)
+from se_unet_airseg_b200.inference import (SlidingWindowPredictor, coverage_counts, exchange_partials, gather_planes,
+                                           owner_ranges, shard_range, split_batches, window_starts)
 
 
 def test_shard_range_partitions_the_window_list():
@@ -63,7 +65,22 @@ def _worker(rank, world, port, out):
     shape, wins, probs = _case()
     lo, hi = shard_range(len(wins), rank, world)
     part = torch.from_numpy(_accumulate(shape, wins[lo:hi], probs[lo:hi], 26).astype(np.int32))
-    dist.reduce(part, dst=0, op=dist.ReduceOp.SUM)                 # the exchange step of predict_device(_shard=...)
+    slabs = []
+    for r in range(world):
+        a, b = shard_range(len(wins), r, world)
+        slabs.append((min(w[0] for w in wins[a:b]), max(w[0] for w in wins[a:b]) + 16) if b > a else (0, 0))
+    owners = owner_ranges(shape[0], world)
+    # planes outside the rank's slab were never written by its windows: poison them to prove they are not used
+    poison = torch.ones_like(part, dtype=torch.bool)
+    poison[slabs[rank][0]:slabs[rank][1]] = False
+    poison[owners[rank][0]:owners[rank][1]] = False
+    part[poison] = 123456789
+    exchange_partials(part, slabs, owners, rank, world)          # the exchange step of predict_device(_shard=...)
+    x0, x1 = owners[rank]
+    own = part[x0:x1].clone()
+    part.fill_(-1)                                               # only the owned planes travel to rank 0
+    part[x0:x1] = own
+    gather_planes(part, owners, rank, world)
     if rank == 0:
         torch.save(part, out)
     dist.destroy_process_group()
@@ -78,12 +95,13 @@ def _case():
     return shape, wins, probs
 
 
-def test_two_rank_integer_partial_volume_reduce_is_bit_exact(tmp_path):
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_partial_plane_exchange_is_bit_exact(tmp_path, world):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     out = str(tmp_path / "acc.pt")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     got = torch.load(out).numpy().astype(np.int64)
     shape, wins, probs = _case()
     want = _accumulate(shape, wins, probs, 26)
@@ -95,3 +113,11 @@ def test_two_rank_integer_partial_volume_reduce_is_bit_exact(tmp_path):
     cx, cy, cz = (coverage_counts(n, window_starts(n, 16, 8), 16) for n in shape)
     assert np.array_equal(cnt, cx[:, None, None] * cy[None, :, None] * cz[None, None, :])
     assert cnt.max() * 2 ** 26 < 2 ** 31
+
+
+def test_owner_ranges_partition_the_first_axis():
+    for n in (40, 400, 512):
+        for world in (1, 2, 3, 4, 8):
+            o = owner_ranges(n, world)
+            assert o[0][0] == 0 and o[-1][1] == n and all(a[1] == b[0] for a, b in zip(o, o[1:]))
+            assert max(b - a for a, b in o) - min(b - a for a, b in o) <= 1
