@@ -9,8 +9,8 @@ One "step" = sliding-window inference of ONE synthetic 512x512x400 CT volume (BA
 sigmoid, overlap mean, 0.5 threshold.  `value` = volume voxels / s with the stored CT volume already resident in
 HBM; `e2e` = the same through the public API (SlidingWindowPredictor.predict) with a pinned HOST volume in and
 the HOST mask out.  N > 1: one process per GPU (torchrun); the 294 windows of the SAME volume are sharded by patch over
-the ranks and the partial probability volumes are summed by one NCCL reduce over NVLink -> strong scaling of the latency of
-one volume (the volume-per-rank sweep without any collective is reported as the secondary key `sweep`); max over ranks.
+the ranks, the partial fixed-point planes go point-to-point (NCCL over NVLink) to the rank that owns them, every rank finalizes
+1/N of the planes and rank 0 collects the mask -> strong scaling of the latency of one volume (the volume-per-rank sweep without any collective is reported as the secondary key `sweep`); max over ranks.
 
 Synthetic data, random-init weights (no datasets/checkpoints in the sandbox).
 """
@@ -379,7 +379,7 @@ def run_ours(args):
     workload = ("sliding-window SE_UNet inference of one synthetic 512x512x400 CT volume (294 windows of 128^3 at stride 64, eval "
                 "mode, threshold 0.5)")
     if sharded:
-        workload += f", windows sharded by patch over {world} GPUs, partial probability volumes summed by one NCCL reduce"
+        workload += f", windows sharded by patch over {world} GPUs, partial planes exchanged point-to-point with their owner ranks (NCCL over NVLink), mask collected on rank 0"
     line = {
         "metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
