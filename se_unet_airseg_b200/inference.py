@@ -161,7 +161,7 @@ class SlidingWindowPredictor:
 
     @torch.no_grad()
     def predict_device(self, img_dev, hu_offset=-1024.0, return_prob=False, reuse_output=False, _slab_events=None,
-                       _shard=None):
+                       _shard=None, _host_out=None):
         """img_dev: (X, Y, Z) int16 or fp32 CUDA tensor holding the stored CT values (HU + 1024, prediction.py:68-69).
         Returns the uint8 mask (X, Y, Z) on the device (and the mean probability if return_prob).
         The results are fresh tensors unless reuse_output=True, which hands out the predictor's own accumulator / mask
@@ -170,7 +170,10 @@ class SlidingWindowPredictor:
         by slab on a copy stream; a window batch waits only for the slabs it reads.
         _shard (internal, used by the *_sharded entry points): (rank, world, group) - run only this rank's range of the
         window list, exchange the partial planes with their owner ranks (exchange_partials), finalize the owned planes and
-        collect the mask on rank 0; ranks != 0 return None."""
+        collect the mask on rank 0; ranks != 0 return None.
+        _host_out (internal, used by predict()): pinned uint8 host tensor - planes are divided, thresholded and copied to the
+        host as soon as the last window that touches them has been issued (the window list is ordered along the first axis),
+        so only the last slab's D2H copy is left after the last forward."""
         L = _lib.lib()
         m = self.model
         if m.in_channel != 2:
@@ -214,6 +217,13 @@ class SlidingWindowPredictor:
             ready.record(main)
             for s_ in streams:
                 s_.wait_event(ready)
+        early = None
+        if _host_out is not None and not sharded:
+            out_stream = getattr(self, "_out_stream", None)
+            if out_stream is None or out_stream.device != dev:
+                out_stream = torch.cuda.Stream(device=dev)
+                self._out_stream = out_stream
+            early = dict(x=0, stream=out_stream, host=_host_out)
         i = 0
         for k, b in enumerate(split_batches(len(wins), self.batch)):
             slot = k % len(streams)
@@ -242,11 +252,22 @@ class SlidingWindowPredictor:
                     _lib.check(L.seunet_window_accumulate(_lib.ptr(pred1), starts, b, cube, cube, cube, _lib.ptr(g["acc"]),
                                                           X, Y, Z, 1, g["acc_log2"], stp), "seunet_window_accumulate")
             i += b
+            if early is not None:
+                # planes below the first-axis origin of the next window are complete once everything issued so far has run
+                x_done = wins[i][0] if i < len(wins) else X
+                if x_done > early["x"]:
+                    self._finalize_slab(g, early, x_done, streams[:min(k + 1, len(streams))], return_prob)
         if self.nstreams > 1:
             for s_ in streams:
                 done = torch.cuda.Event()
                 done.record(s_)
                 main.wait_event(done)
+        if early is not None:
+            main.wait_stream(early["stream"])
+            prob = g["acc"].view(torch.float32)
+            if reuse_output:
+                return (g["mask"], prob) if return_prob else g["mask"]
+            return (g["mask"].clone(), prob.clone()) if return_prob else g["mask"].clone()
         if sharded:
             # the exchange step of patch sharding (NCCL point-to-point over NVLink/NVSwitch): partial planes go to the rank
             # that finalizes them; every rank divides / thresholds its own planes; rank 0 collects the uint8 mask planes
@@ -277,6 +298,28 @@ class SlidingWindowPredictor:
         if reuse_output:
             return (g["mask"], prob) if return_prob else g["mask"]
         return (g["mask"].clone(), prob.clone()) if return_prob else g["mask"].clone()
+
+    def _finalize_slab(self, g, early, x_done, used_streams, write_mean):
+        """Divide / threshold planes [early.x, x_done) on the output stream once the work issued so far on `used_streams` has
+        finished, and start their D2H copy (prediction.py:109-110 applied slab by slab: the operations are per voxel)."""
+        L = _lib.lib()
+        x0, out_stream = early["x"], early["stream"]
+        X, Y, Z = g["acc"].shape
+        for s_ in used_streams:
+            ev = torch.cuda.Event()
+            ev.record(s_)
+            out_stream.wait_event(ev)
+        key = ("counts_slab", x0, x_done)
+        if key not in g:
+            g[key] = torch.cat([g["counts"][x0:x_done], g["counts"][X:]]).contiguous()
+        plane = Y * Z
+        with torch.cuda.stream(out_stream):
+            _lib.check(L.seunet_window_finalize(ctypes.c_void_p(g["acc"].data_ptr() + x0 * plane * 4), _lib.ptr(g[key]),
+                                                x_done - x0, Y, Z, float(self.threshold),
+                                                ctypes.c_void_p(g["mask"].data_ptr() + x0 * plane), 1 if write_mean else 0,
+                                                g["acc_log2"], ctypes.c_void_p(out_stream.cuda_stream)), "seunet_window_finalize")
+            early["host"][x0:x_done].copy_(g["mask"][x0:x_done], non_blocking=True)
+        early["x"] = x_done
 
     # ------------------------------------------------------------------------------------------
     # patch-sharded inference of one volume over the ranks of a process group (one process per GPU)
@@ -335,7 +378,8 @@ class SlidingWindowPredictor:
         """End-to-end call a user makes: host volume (numpy int16/float32 or CPU tensor, ideally pinned) in, host uint8
         mask out.  The H2D copy and the HU windowing run slab by slab (along the first axis) on a copy stream, and every window
         batch waits only for the slabs it reads, so the forward passes start after the first ~128 planes have arrived;
-        one D2H copy of the mask at the end.
+        the mask goes back slab by slab as well: planes are finalized and copied to the host as soon as their last window
+        has run, only the last slab's copy follows the last forward.
         Returns a fresh CPU tensor.  reuse_output=True returns the predictor's pinned staging buffer instead (no host
         copy); it is OVERWRITTEN by the next predict() of a same-shaped volume - only for callers that consume the mask
         before the next call (prediction.py does: it writes the NIfTI, then moves on)."""
@@ -373,14 +417,17 @@ class SlidingWindowPredictor:
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 events.append((x1, ev))
-        mask = self.predict_device(stage, hu_offset, reuse_output=True, _slab_events=events, _shard=_shard)
+        out = getattr(self, "_host_mask", None)
+        single = _shard is None or _shard[1] <= 1
+        if (single or _shard[0] == 0) and (out is None or tuple(out.shape) != (X, Y, Z)):
+            out = torch.empty((X, Y, Z), dtype=torch.uint8, pin_memory=True)
+            self._host_mask = out
+        mask = self.predict_device(stage, hu_offset, reuse_output=True, _slab_events=events, _shard=_shard,
+                                   _host_out=out if single else None)
         if mask is None:            # sharded call on a rank != 0
             torch.cuda.current_stream(dev).synchronize()
             return None
-        out = getattr(self, "_host_mask", None)
-        if out is None or out.shape != mask.shape:
-            out = torch.empty(mask.shape, dtype=torch.uint8, pin_memory=True)
-            self._host_mask = out
-        out.copy_(mask, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        if not single:
+            out.copy_(mask, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()   # (single GPU: the slab copies were joined into this stream)
         return out if reuse_output else out.clone()
