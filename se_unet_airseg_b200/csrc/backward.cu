@@ -11,17 +11,41 @@ constexpr float kInEps = 1e-5f;
 __device__ __forceinline__ float lrelu_grad(float n) { return n > 0.f ? 1.f : 0.01f; }
 __device__ __forceinline__ void atomic_max_pos(unsigned int* p, float v) { atomicMax(p, __float_as_uint(v)); }
 
+// per-layer power-of-two pre-scaling of dY (the 16-bit operand of the tensor-core dgrad / wgrad), from max |dn * rstd|
+__device__ __forceinline__ float dy_scale_from_max(unsigned int bits) {
+  const float mx = __uint_as_float(bits);
+  if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
+  float e = 8.f - ceilf(log2f(mx));          // largest |dn*rstd| lands in [2^7, 2^8]
+  e = fminf(fmaxf(e, -100.f), 100.f);
+  return exp2f(e);
+}
+
 // =============================================================================================
-// SSE block backward, pass A
+// SSE block backward.  PASS 0: pass A (gate / activation backward + per-(n,c) reductions) writing dn for the generic pass B
+// (norm_bwd_b_kernel).  PASS 1 / PASS 2 (round 2, late): the same pass A WITHOUT the dn store, and a pass B that RECOMPUTES dn
+// from the same inputs with the same instruction sequence and writes dY directly - dn never touches HBM: per element and
+// channel 6 B read in pass A' and 6 B read + 2 B written in pass B' instead of 6 + 4 and 6 + 2 (dn is fp32).
 // =============================================================================================
-template <int C, int GATES, int PF>
+template <int C, int GATES, int PF, int PASS>
 __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant__ SseBwdArgs a) {
   constexpr int LPV = C / 8;     // lanes cooperating on one voxel (one 8-channel chunk each)
   constexpr int VPW = 32 / LPV;  // voxels per warp
   __shared__ float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
-  __shared__ float s_red[8][5][C];
+  __shared__ float s_red[PASS == 2 ? 1 : 8][5][C];
   __shared__ float s_cst[8], s_max[8];
+  __shared__ float s_m1[PASS == 2 ? C : 1], s_m2[PASS == 2 ? C : 1], s_scale;
   const int n = blockIdx.y;
+  if (PASS == 2) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      s_m1[c] = (float)(a.redS[((size_t)n * 64 + c) * 2] / (double)a.V);
+      s_m2[c] = (float)(a.redS[((size_t)n * 64 + c) * 2 + 1] / (double)a.V);
+    }
+    if (threadIdx.x == 255) {
+      const float sc = dy_scale_from_max(*a.dymax);
+      s_scale = sc;
+      if (blockIdx.x == 0 && n == 0) { a.scale_out[0] = sc; a.scale_out[1] = 1.f / sc; }
+    }
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double s = a.stats[((size_t)n * a.stats_c + c) * 2], q = a.stats[((size_t)n * a.stats_c + c) * 2 + 1];
     const double mean = s / (double)a.V;
@@ -112,15 +136,27 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
       const int c = k * 8 + i;
       const float da = fmaf(s_wse[c], k1, da1[i] * g1);
       dn[i] = da * lrelu_grad(nn[i]);
-      S1[i] += dn[i];
-      S2[i] = fmaf(dn[i], nn[i], S2[i]);
-      Wse[i] = fmaf(k1, av[i], Wse[i]);
-      Wse2[i] = fmaf(k2, a1[i], Wse2[i]);
-      Weff[i] = fmaf(dT, e0[i], Weff[i]);
-      mx = fmaxf(mx, fabsf(dn[i] * s_rstd[c]));
+      if (PASS != 2) {
+        S1[i] += dn[i];
+        S2[i] = fmaf(dn[i], nn[i], S2[i]);
+        Wse[i] = fmaf(k1, av[i], Wse[i]);
+        Wse2[i] = fmaf(k2, a1[i], Wse2[i]);
+        Weff[i] = fmaf(dT, e0[i], Weff[i]);
+        mx = fmaxf(mx, fabsf(dn[i] * s_rstd[c]));
+      }
     }
-    if (k == 0) cst += dT;
-    st_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
+    if (PASS == 0) st_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
+    if (PASS == 2) {   // InstanceNorm backward on the recomputed dn (same arithmetic as norm_bwd_b_kernel)
+      const float sc = s_scale;
+      float dy[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = k * 8 + i;
+        const float t = s_rstd[c] * (dn[i] - s_m1[c] - nn[i] * s_m2[c]) * sc;
+        dy[i] = fminf(fmaxf(t, -60000.f), 60000.f);
+      }
+      st_chunk(a.dy + (((size_t)n * a.dy_chunks + k) * a.V + v) * 8, floats_to_chunk(dy));
+    } else if (k == 0) cst += dT;
   };
   // V is a multiple of 32, so the whole warp is in range whenever its first voxel is
   const long long vb0 = ((long long)blockIdx.x * 8 + warp) * VPW;
@@ -136,6 +172,7 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
     if (vb + PF * vstep < a.V) prefetch(pre[PF - 1], vb + PF * vstep + vsub);
     process(cur, vb + vsub);
   }
+  if (PASS == 2) return;
   // reduce over the voxel sub-lanes of the warp, then over warps, then one atomic per value per block
   auto wreduce = [&](float v) {
 #pragma unroll
@@ -175,51 +212,51 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
 
 template <int C> constexpr bool kSseBwdDeep = false;   // measured: depth 2 spills (128 registers) and is 10-30 % slower
 
-template <int C>
-static int launch_sse_bwd_a_c(const SseBwdArgs& a, cudaStream_t st) {
+template <int C, int PASS>
+static int launch_sse_bwd_c(const SseBwdArgs& a, cudaStream_t st) {
   constexpr int VPB = 8 * (32 / (C / 8));
   const long long need = (a.V + VPB - 1) / VPB;
   // Every block ends with 5*C same-address atomics per sample: at the coarse levels (few voxels) thousands of one-iteration
   // blocks spent their time in that tail and in the per-block statistics prologue.  Give each warp >= 16 voxel groups, but
   // keep >= 4 blocks per SM in flight over the whole batch.
-  const long long floor_blocks = (148 * 4 + a.N - 1) / a.N;
+  static const int floor_per_sm = getenv("SEUNET_BWDA_FLOOR") ? std::max(1, atoi(getenv("SEUNET_BWDA_FLOOR"))) : 4;   // A/B knob
+  const long long floor_blocks = (148 * floor_per_sm + a.N - 1) / a.N;
   const long long gx = std::min<long long>(need, std::max<long long>(floor_blocks, std::min<long long>(148 * 8, need / 16)));
   dim3 grid((unsigned)gx, a.N);
   // prefetch depth 2 only where the one-group-ahead version is short of bytes in flight (A/B, tools/r02_call50.sh)
   static const int pf_env = getenv("SEUNET_BWDA_PF") ? atoi(getenv("SEUNET_BWDA_PF")) : 0;
-  const bool deep = pf_env ? pf_env == 2 : kSseBwdDeep<C>;
+  const bool deep = PASS == 0 && (pf_env ? pf_env == 2 : kSseBwdDeep<C>);
   if (deep) {
-    if (a.wse2) sse_bwd_a_kernel<C, 2, 2><<<grid, 256, 0, st>>>(a);
-    else sse_bwd_a_kernel<C, 1, 2><<<grid, 256, 0, st>>>(a);
+    if (a.wse2) sse_bwd_a_kernel<C, 2, 2, 0><<<grid, 256, 0, st>>>(a);
+    else sse_bwd_a_kernel<C, 1, 2, 0><<<grid, 256, 0, st>>>(a);
   } else {
-    if (a.wse2) sse_bwd_a_kernel<C, 2, 1><<<grid, 256, 0, st>>>(a);
-    else sse_bwd_a_kernel<C, 1, 1><<<grid, 256, 0, st>>>(a);
+    if (a.wse2) sse_bwd_a_kernel<C, 2, 1, PASS><<<grid, 256, 0, st>>>(a);
+    else sse_bwd_a_kernel<C, 1, 1, PASS><<<grid, 256, 0, st>>>(a);
   }
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
-int launch_sse_bwd_a(int C, const SseBwdArgs& a, cudaStream_t st) {
+template <int C>
+static int launch_sse_bwd_p(const SseBwdArgs& a, int pass, cudaStream_t st) {
+  if (pass == 0) return launch_sse_bwd_c<C, 0>(a, st);
+  if (pass == 1) return launch_sse_bwd_c<C, 1>(a, st);
+  if (!a.dy || !a.scale_out) { seunet_set_error("sse_bwd: pass B needs dy and scale_out"); return 1; }
+  return launch_sse_bwd_c<C, 2>(a, st);
+}
+int launch_sse_bwd(int C, const SseBwdArgs& a, int pass, cudaStream_t st) {
   switch (C) {
-    case 8: return launch_sse_bwd_a_c<8>(a, st);
-    case 16: return launch_sse_bwd_a_c<16>(a, st);
-    case 32: return launch_sse_bwd_a_c<32>(a, st);
-    case 64: return launch_sse_bwd_a_c<64>(a, st);
+    case 8: return launch_sse_bwd_p<8>(a, pass, st);
+    case 16: return launch_sse_bwd_p<16>(a, pass, st);
+    case 32: return launch_sse_bwd_p<32>(a, pass, st);
+    case 64: return launch_sse_bwd_p<64>(a, pass, st);
   }
-  seunet_set_error("sse_bwd_a: C=%d unsupported", C);
+  seunet_set_error("sse_bwd: C=%d unsupported", C);
   return 1;
 }
 
 // =============================================================================================
 // InstanceNorm backward, pass B (shared by SSE and CAT blocks)
 // =============================================================================================
-__device__ __forceinline__ float dy_scale_from_max(unsigned int bits) {
-  const float mx = __uint_as_float(bits);
-  if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
-  float e = 8.f - ceilf(log2f(mx));          // largest |dn*rstd| lands in [2^7, 2^8]
-  e = fminf(fmaxf(e, -100.f), 100.f);
-  return exp2f(e);
-}
-
 __global__ void __launch_bounds__(256) norm_bwd_b_kernel(const __grid_constant__ NormBwdArgs a) {
   __shared__ float s_mean[8], s_rstd[8], s_m1[8], s_m2[8];
   __shared__ float s_scale;

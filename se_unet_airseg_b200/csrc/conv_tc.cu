@@ -490,6 +490,35 @@ struct PackArgs {
   PackStep steps[kConvMaxSteps];
 };
 
+// One element of the packed image: image index i of a layer described by `p`, whose K=16 step s maps to taps / channel
+// bases `ps`.  Shared by the single-layer kernel (stand-alone conv API, tests) and the batched one (plans).
+template <class P>
+__device__ __forceinline__ uint16_t pack_element(const float* __restrict__ w, const P& p, const PackStep ps, int c, int khalf, int row, int e) {
+  const int tap = khalf ? ps.tap_b : ps.tap_a;
+  const int ci = c * p.KC + (khalf ? ps.cbase_b : ps.cbase_a) + e;
+  const int jkd = row / p.COUT, co = row % p.COUT;
+  float val = 0.f;
+  if (tap >= 0) {
+    int kd = (p.nkd == 3) ? (2 - jkd) : 0;
+    int kh = tap / 3, kw = tap % 3;
+    const int K = p.ksize, K3 = K * K * K;
+    if (!p.transpose_flip) {
+      if (co < p.Cout_real && ci < p.Cin_real)
+        val = w[((size_t)co * p.Cin_real + ci) * K3 + (kd * K + kh) * K + kw];
+    } else {
+      // data gradient: "input" channels are the forward Cout, "output" channels the forward Cin,
+      // taps mirrored.  Cin_real/Cout_real are given in the gradient operator's own roles.
+      if (co < p.Cout_real && ci < p.Cin_real) {
+        if (K == 3) { kd = 2 - kd; kh = 2 - kh; kw = 2 - kw; }
+        val = w[((size_t)ci * p.co_total + p.co_off + co) * K3 + (kd * K + kh) * K + kw];
+      }
+    }
+  }
+  if (p.bf16) { __nv_bfloat16 b = __float2bfloat16_rn(val); return *reinterpret_cast<uint16_t*>(&b); }
+  act_t h = f2act(val);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
 __global__ void conv_pack_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, const __grid_constant__ PackArgs p) {
   const int rows = p.nkd * p.COUT;
   const size_t total = (size_t)p.nchunks * p.nsteps * 2 * rows * 8;
@@ -499,30 +528,39 @@ __global__ void conv_pack_kernel(const float* __restrict__ w, uint16_t* __restri
     const int row = r % rows; r /= rows;
     const int khalf = r % 2; r /= 2;
     const int s = r % p.nsteps; r /= p.nsteps;
-    const int c = (int)r;
-    const PackStep ps = p.steps[s];
-    const int tap = khalf ? ps.tap_b : ps.tap_a;
-    const int ci = c * p.KC + (khalf ? ps.cbase_b : ps.cbase_a) + e;
-    const int jkd = row / p.COUT, co = row % p.COUT;
-    float val = 0.f;
-    if (tap >= 0) {
-      int kd = (p.nkd == 3) ? (2 - jkd) : 0;
-      int kh = tap / 3, kw = tap % 3;
-      const int K = p.ksize, K3 = K * K * K;
-      if (!p.transpose_flip) {
-        if (co < p.Cout_real && ci < p.Cin_real)
-          val = w[((size_t)co * p.Cin_real + ci) * K3 + (kd * K + kh) * K + kw];
-      } else {
-        // data gradient: "input" channels are the forward Cout, "output" channels the forward Cin,
-        // taps mirrored.  Cin_real/Cout_real are given in the gradient operator's own roles.
-        if (co < p.Cout_real && ci < p.Cin_real) {
-          if (K == 3) { kd = 2 - kd; kh = 2 - kh; kw = 2 - kw; }
-          val = w[((size_t)ci * p.co_total + p.co_off + co) * K3 + (kd * K + kh) * K + kw];
-        }
-      }
+    img[i] = pack_element(w, p, p.steps[s], (int)r, khalf, row, e);
+  }
+}
+
+// All layers of a plan in one launch (blockIdx.y = layer): a training step re-packs ~70 images (forward convs + the
+// mirrored data-gradient pieces) after every optimizer step, and at one patch per rank 70 launches of a few microseconds
+// each were 3 % of the step.  The step table is a function of (paired, KC) only (conv_geom_init), so a job is 72 bytes and
+// 48 of them travel as kernel parameters.
+struct PackBatch { ConvPackJob job[kConvPackBatch]; };
+
+__global__ void __launch_bounds__(256) conv_pack_batch_kernel(const float* __restrict__ params, uint8_t* __restrict__ wimg,
+                                                              const __grid_constant__ PackBatch b) {
+  const ConvPackJob& p = b.job[blockIdx.y];
+  const float* w = params + p.src_off;
+  uint16_t* img = reinterpret_cast<uint16_t*>(wimg + p.dst_off);
+  const unsigned rows = (unsigned)(p.nkd * p.COUT), nsteps = (unsigned)p.nsteps, jsteps = (unsigned)(p.KC / 16);
+  const unsigned total = (unsigned)p.nchunks * nsteps * 2u * rows * 8u;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    unsigned r = i;
+    const int e = (int)(r % 8u); r /= 8u;
+    const int row = (int)(r % rows); r /= rows;
+    const int khalf = (int)(r % 2u); r /= 2u;
+    const int s = (int)(r % nsteps); r /= nsteps;
+    PackStep ps;   // the same table conv_geom_init writes into ConvGeom::psteps
+    if (p.paired) {
+      ps.tap_a = (int8_t)(s == 0 ? 0 : 2 * s - 1); ps.tap_b = (int8_t)(s == 0 ? -1 : 2 * s);
+      ps.cbase_a = 0; ps.cbase_b = 0;
+    } else {
+      const int t = s / (int)jsteps, j = s % (int)jsteps;
+      ps.tap_a = ps.tap_b = (int8_t)t;
+      ps.cbase_a = (int16_t)(j * 16); ps.cbase_b = (int16_t)(j * 16 + 8);
     }
-    if (p.bf16) { __nv_bfloat16 b = __float2bfloat16_rn(val); img[i] = *reinterpret_cast<uint16_t*>(&b); }
-    else { act_t h = f2act(val); img[i] = *reinterpret_cast<uint16_t*>(&h); }
+    img[i] = pack_element(w, p, ps, (int)r, khalf, row, e);
   }
 }
 
@@ -636,6 +674,30 @@ int conv_pack_weights(const ConvGeom& g, const float* w_fp32, void* wimg, int tr
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 1024);
   conv_pack_kernel<<<blocks, 256, 0, st>>>(w_fp32, (uint16_t*)wimg, p);
   SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+ConvPackJob conv_pack_job(const ConvGeom& g, long long src_off, long long dst_off, int transpose_flip, int co_off, int co_total) {
+  ConvPackJob j;
+  memset(&j, 0, sizeof(j));
+  j.src_off = src_off; j.dst_off = dst_off;
+  j.Cin_real = g.Cin_real; j.Cout_real = g.Cout_real; j.COUT = g.COUT; j.ksize = g.ksize;
+  j.nkd = g.ksize == 3 ? 3 : 1; j.KC = g.KC; j.nchunks = g.nchunks; j.nsteps = g.nsteps;
+  j.transpose_flip = transpose_flip; j.bf16 = g.bf16;
+  j.co_off = co_off; j.co_total = co_total < 0 ? g.Cout_real : co_total;
+  j.paired = g.paired ? 1 : 0;
+  return j;
+}
+
+int conv_pack_weights_batch(const ConvPackJob* jobs, int njobs, const float* params, void* wimg, cudaStream_t st) {
+  for (int j0 = 0; j0 < njobs; j0 += kConvPackBatch) {
+    PackBatch b;
+    const int nb = std::min(kConvPackBatch, njobs - j0);
+    memset(&b, 0, sizeof(b));
+    memcpy(b.job, jobs + j0, sizeof(ConvPackJob) * nb);
+    conv_pack_batch_kernel<<<dim3(48, nb), 256, 0, st>>>(params, (uint8_t*)wimg, b);
+    SEUNET_CUDA_CHECK(cudaGetLastError());
+  }
   return 0;
 }
 

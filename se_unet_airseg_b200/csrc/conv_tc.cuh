@@ -80,6 +80,16 @@ int conv_geom_init(ConvGeom* g, int Cin_real, int Cout_real, int ksize, int dil,
 int conv_pack_weights(const ConvGeom& g, const float* w_fp32, void* wimg, int transpose_flip, cudaStream_t st,
                       int co_off = 0, int co_total = -1);
 
+// Batched packing (plans): every job describes one layer image; sources are offsets into ONE flat fp32 parameter buffer,
+// destinations byte offsets into ONE packed-image buffer.  kConvPackBatch jobs per launch (kernel-parameter space).
+constexpr int kConvPackBatch = 48;
+struct ConvPackJob {
+  long long src_off, dst_off;
+  int Cin_real, Cout_real, COUT, ksize, nkd, KC, nchunks, nsteps, transpose_flip, bf16, co_off, co_total, paired, pad_;
+};
+ConvPackJob conv_pack_job(const ConvGeom& g, long long src_off, long long dst_off, int transpose_flip, int co_off = 0, int co_total = -1);
+int conv_pack_weights_batch(const ConvPackJob* jobs, int njobs, const float* params, void* wimg, cudaStream_t st);
+
 struct ConvLaunch {
   ConvGeom g;
   CUtensorMap tmap;

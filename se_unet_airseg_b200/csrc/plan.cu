@@ -171,9 +171,11 @@ struct seunet_plan {
   uint8_t* wimg = nullptr;
   XOffsets xo;                      // per-sample input offsets of the current forward
   // backward concurrency (plan_bwd.inc): plan-owned side streams forked from / joined to the caller's stream with events.
-  // side[0] carries the weight gradients, side[1..3] the extra dgrad pieces of layers wider than 64 channels.
-  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_side[4] = {nullptr, nullptr, nullptr, nullptr};
+  // side[0] carries the weight gradients, side[1..3] the extra dgrad pieces of layers wider than 64 channels, side[4] the
+  // adjoint of the heads' folded side-branch up-sampling (needed only when the backward reaches level 1).
+  static constexpr int kSideStreams = 5;
+  cudaStream_t side[kSideStreams] = {};
+  cudaEvent_t ev_fork = nullptr, ev_side[kSideStreams] = {};
   bool wg_pending = false;          // a wgrad on side[0] has not been joined to the caller's stream yet
   long long conc_vox = 0;           // layers with batch * voxels <= conc_vox use the side streams (0: never)
   // optional per-launch CUDA-event timing (bench roofline); events live on the caller's stream
@@ -196,7 +198,7 @@ static size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 // backward-pass planning hooks (plan_bwd.inc)
 static int bwd_plan_create(seunet_plan* p, size_t& wimg, size_t& off);
 static int bwd_plan_bind(seunet_plan* p);
-static int bwd_pack_weights(seunet_plan* p, const float* params, cudaStream_t st);
+static void bwd_pack_jobs(seunet_plan* p, std::vector<ConvPackJob>& jobs);
 
 extern "C" int seunet_version(void) { return 1; }
 extern "C" int seunet_act_dtype(void) {
@@ -327,7 +329,7 @@ extern "C" int seunet_plan_create(seunet_plan_t** out, int batch, int D, int H, 
 extern "C" void seunet_plan_destroy(seunet_plan_t* p) {
   if (!p) return;
   for (auto e : p->ev) cudaEventDestroy(e);
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < seunet_plan::kSideStreams; ++i) {
     if (p->ev_side[i]) cudaEventDestroy(p->ev_side[i]);
     if (p->side[i]) cudaStreamDestroy(p->side[i]);
   }
@@ -426,12 +428,13 @@ extern "C" int seunet_plan_bind(seunet_plan_t* p, void* workspace, void* wimg, s
 extern "C" int seunet_pack_weights(seunet_plan_t* p, const float* params, seunet_stream_t stream) {
   if (!p || !p->wimg) { seunet_set_error("pack_weights: plan not bound"); return 1; }
   cudaStream_t st = (cudaStream_t)stream;
-  for (int i = 0; i < 18; ++i)
-    if (conv_pack_weights(p->sse_conv[i].g, params + p->sse_conv[i].w_off, p->wimg + p->sse_conv[i].wimg_off, 0, st)) return 1;
-  for (int i = 0; i < 6; ++i)
-    if (conv_pack_weights(p->cat_conv[i].g, params + p->cat_conv[i].w_off, p->wimg + p->cat_conv[i].wimg_off, 0, st)) return 1;
-  if (p->mode == 1 && bwd_pack_weights(p, params, st)) return 1;
-  return 0;
+  // every layer image of the plan (forward convs, and in training plans the mirrored data-gradient pieces) in one batched
+  // launch per kConvPackBatch layers
+  std::vector<ConvPackJob> jobs;
+  for (int i = 0; i < 18; ++i) jobs.push_back(conv_pack_job(p->sse_conv[i].g, p->sse_conv[i].w_off, (long long)p->sse_conv[i].wimg_off, 0));
+  for (int i = 0; i < 6; ++i) jobs.push_back(conv_pack_job(p->cat_conv[i].g, p->cat_conv[i].w_off, (long long)p->cat_conv[i].wimg_off, 0));
+  if (p->mode == 1) bwd_pack_jobs(p, jobs);
+  return conv_pack_weights_batch(jobs.data(), (int)jobs.size(), params, p->wimg, st);
 }
 
 // ---------------------------------------------------------------------------------------------
