@@ -47,7 +47,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKArgs& a, int tile) {
   t.par = 0;
   if (a.dstep == 2) { const int half = a.tilesD >> 1; t.par = td >= half ? 1 : 0; td -= t.par * half; }
   t.Dp = a.dstep == 2 ? ((a.D - t.par + 1) >> 1) : a.D;
-  t.n = tile; t.d0 = td * DT; t.h0 = th * kConvTileH; t.w0 = tw * kConvTileW;
+  t.n = tile; t.d0 = td * a.dt_use; t.h0 = th * kConvTileH; t.w0 = tw * kConvTileW;
   return t;
 }
 
@@ -326,7 +326,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             PROF_T0(tw); mbar_wait(wfull_bar(slot), (wcount / a.wslots) & 1u); PROF_ADD(i_w, tw);
           }
           const uint32_t b_lo_slot = b_lo_lbo | (((w_addr + slot * a.wchunk_bytes) & 0x3FFFFu) >> 4);
-          const int kv0 = max(0, -q0 - t.d0), kv1 = D - 1 - t.d0 - q0;   // planes inside the volume (k = q - q0)
+          // planes inside the volume (k = q - q0) that feed the dt_use output planes this tile owns (shallow tiles, see
+          // conv_launch_init: the planes behind them are loaded but not multiplied)
+          const int kv0 = max(0, -q0 - t.d0), kv1 = min(D - 1 - t.d0 - q0, a.dt_use - 1 - 2 * q0);
 #define SEUNET_ISSUE_TILE(M) issue_tile<COUT, M>(ring, a_lo_first, full_bar(0), a.nstages, stage16, plane16, pb, kv0, kv1, c == 0, \
                                                  c == last_chunk, tphase, tmem_base, tempty_bar(0), tfull_bar(0), idesc1, idesc_clear, \
                                                  zdesc, a_hi, b_hi, b_lo_slot, j_step, b_step, jsteps, a.dlt)
@@ -388,7 +390,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       if (t.n != run_n) { flush_stats(); run_n = t.n; }
       const int h = t.h0 + hh, w = t.w0 + ww;
       const bool inb = (h < a.H) && (w < a.W);
-      const int dteff = min(DT, t.Dp - t.d0);
+      const int dteff = min(a.dt_use, t.Dp - t.d0);
       // per-lane partial sums of this tile: red[cg*32 + i] = sum of channel cg*16+i, red[cg*32 + 16 + i] = sum of squares
       float red[2 * COUT];
 #pragma unroll
@@ -721,7 +723,7 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
                      const void* in, int in_chunks_total, int in_chunk_off,
                      void* out, int out_chunks_total, int out_chunk_off,
                      double* stats, const void* wimg, int num_sms, int accum_out, int out_real_chunks, int grad_out,
-                     const float* out_scale) {
+                     const float* out_scale, int shallow_ok) {
   L->g = g;
   ConvKArgs& a = L->a;
   memset(&a, 0, sizeof(a));
@@ -735,7 +737,27 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
   a.tilesH = (H + kConvTileH - 1) / kConvTileH;
   // dilation 2: split the planes into the two parity classes (plane distance of the kd taps becomes 1 inside a class)
   a.dstep = (nkd == 3 && g.dil == 2) ? 2 : 1;
-  a.tilesD = a.dstep == 2 ? 2 * (((D + 1) / 2 + DT - 1) / DT) : (D + DT - 1) / DT;
+  auto tiles_d = [&](int dt) { return a.dstep == 2 ? 2 * (((D + 1) / 2 + dt - 1) / dt) : (D + dt - 1) / dt; };
+  // Shallow tiles: a CTA tile normally owns DT output planes (the whole TMEM), which leaves most SMs idle when the layer has
+  // fewer tiles than SMs - a 16^3 level of one patch is FOUR tiles of 10 sequential input planes each (30 us whatever the
+  // batch size up to 8).  With dt_use < DT a tile owns only its first dt_use planes: the schedule (boxes, accumulator groups)
+  // is unchanged, the MMAs of the input planes behind plane dt_use + 1 are skipped and their accumulators never stored, so
+  // a tile costs ~(dt_use + 2) planes of MMAs and there are DT/dt_use times as many tiles.  Per output voxel the accumulation
+  // order is the same, so the result is bit-identical; only launches WITHOUT InstanceNorm statistics use it (data gradients):
+  // the per-tile fp32 statistics partials of the forward convs would otherwise depend on the batch size.
+  int dtu = DT;
+  static const bool shallow_env = !(getenv("SEUNET_CONV_SHALLOW") && atoi(getenv("SEUNET_CONV_SHALLOW")) == 0);   // A/B knob
+  if (shallow_ok && shallow_env && stats == nullptr) {
+    const int extra = (nkd == 3 ? 2 : 0) + 3;   // halo planes + per-tile fixed cost (pipeline fill, weight ring) in plane units
+    long best = -1;
+    for (int dt = DT; dt >= 2; --dt) {
+      const long tiles = (long)a.tilesW * a.tilesH * tiles_d(dt) * N;
+      const long cost = ((tiles + num_sms - 1) / num_sms) * (dt + extra);
+      if (best < 0 || cost < best) { best = cost; dtu = dt; }
+    }
+  }
+  a.dt_use = dtu;
+  a.tilesD = tiles_d(dtu);
   a.numTiles = a.tilesW * a.tilesH * a.tilesD * N;
   a.dil = nkd == 3 ? (a.dstep == 2 ? 1 : g.dil) : 0;
   a.nkd = nkd; a.halo = halo;

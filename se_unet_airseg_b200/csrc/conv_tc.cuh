@@ -25,6 +25,7 @@ struct ConvKArgs {
   int out_chunks_total, out_chunk_off;
   int nstages, wslots, nsteps;
   int pb, nboxes;        // planes per TMA box (= ring stage) and boxes per (tile, channel chunk)
+  int dt_use;            // output planes a tile owns (<= DT = 512/COUT; < DT: shallow tiles of small layers)
   int dbg;               // developer experiment flags (only read by -DSEUNET_CONV_PROFILE builds)
   int cdil;              // the conv's own dilation (1|2; tap offsets inside the halo tile), 0 for 1x1x1
   uint32_t plane16;      // one halo plane inside a box, in 16-byte units
@@ -103,5 +104,6 @@ int conv_launch_init(ConvLaunch* L, const ConvGeom& g, int N, int D, int H, int 
                      const void* in, int in_chunks_total, int in_chunk_off,
                      void* out, int out_chunks_total, int out_chunk_off,
                      double* stats, const void* wimg, int num_sms, int accum_out = 0, int out_real_chunks = -1,
-                     int grad_out = 0 /* 1: output is grad_t */, const float* out_scale = nullptr);
+                     int grad_out = 0 /* 1: output is grad_t */, const float* out_scale = nullptr,
+                     int shallow_ok = 0 /* 1: tiles may own fewer than DT planes when the layer cannot fill the SMs */);
 int conv_launch_run(const ConvLaunch& L, cudaStream_t st);

@@ -704,7 +704,7 @@ extern "C" int seunet_conv_fprop(const void* in, int in_chunks, int in_chunk_off
   ConvLaunch L;
   if (accum_out && !grad_out) { seunet_set_error("conv_fprop: accum_out needs grad_out"); return 1; }
   if (conv_launch_init(&L, g, N, D, H, W, in, in_chunks, in_chunk_off, out, (Cout + 7) / 8, 0, stats, scratch, sms, accum_out,
-                       (Cout + 7) / 8, grad_out))
+                       (Cout + 7) / 8, grad_out, nullptr, /*shallow_ok=*/grad_out))   // gradient-format launches tile like the plans' dgrads
     return 1;
   return conv_launch_run(L, st);
 }
