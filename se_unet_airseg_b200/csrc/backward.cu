@@ -4,6 +4,7 @@
 #include "backward.cuh"
 #include <algorithm>
 #include <cstring>
+#include <cstdint>
 #include <cstdlib>
 
 constexpr float kInEps = 1e-5f;
@@ -26,10 +27,31 @@ __device__ __forceinline__ float dy_scale_from_max(unsigned int bits) {
 // from the same inputs with the same instruction sequence and writes dY directly - dn never touches HBM: per element and
 // channel 6 B read in pass A' and 6 B read + 2 B written in pass B' instead of 6 + 4 and 6 + 2 (dn is fp32).
 // =============================================================================================
-template <int C, int GATES, int PF, int PASS>
+// RING > 0 (round 2, late): the inputs of a warp's next RING voxel groups are in flight as bulk copies (cp.async.bulk, one
+// mbarrier per warp and ring slot) into a warp-private shared-memory ring instead of as register prefetch: the kernel runs
+// at 25 % occupancy, so the bytes in flight per SM - 26 KB with one group ahead in registers, which by Little's law caps the
+// read rate near 3 TB/s; two groups ahead spill - decide the bandwidth, and a ring slot costs no registers.
+template <int C> struct SseRing {
+  static constexpr int LPV = C / 8, VPW = 32 / LPV;
+  static constexpr int GB = 8 * (int)sizeof(grad_t);          // bytes of one gradient chunk
+  static constexpr int RS_RAW = VPW * 16 + 16;                // row (one chunk plane, VPW voxels) + 16 B against bank conflicts
+  static constexpr int RS_DE0 = VPW * GB + 16;
+  static constexpr int DE0_OFF = LPV * RS_RAW;
+  static constexpr int DT_OFF = DE0_OFF + LPV * RS_DE0;
+  static constexpr int STAGE = (DT_OFF + 128 + 127) / 128 * 128;
+};
+constexpr int kSseRingDepth = 4;
+
+template <int C, int GATES, int PF, int PASS, int RING>
 __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant__ SseBwdArgs a) {
   constexpr int LPV = C / 8;     // lanes cooperating on one voxel (one 8-channel chunk each)
   constexpr int VPW = 32 / LPV;  // voxels per warp
+  extern __shared__ __align__(128) uint8_t s_ring[];          // RING > 0: [8 warps][RING][SseRing<C>::STAGE]
+  __shared__ __align__(8) unsigned long long s_bar[8 * (RING > 0 ? RING : 1)];
+  if (RING > 0) {
+    if (threadIdx.x < 8 * RING) mbar_init(smem_u32(&s_bar[threadIdx.x]), 1);
+    fence_mbar_init();
+  }
   __shared__ float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
   __shared__ float s_red[PASS == 2 ? 1 : 8][5][C];
   __shared__ float s_cst[8], s_max[8];
@@ -160,17 +182,71 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
   };
   // V is a multiple of 32, so the whole warp is in range whenever its first voxel is
   const long long vb0 = ((long long)blockIdx.x * 8 + warp) * VPW;
-  Pre pre[PF];
+  if constexpr (RING > 0) {
+    using R = SseRing<C>;
+    const uint32_t ring0 = smem_u32(s_ring) + (uint32_t)(warp * RING * R::STAGE);
+    const uint32_t bar0 = smem_u32(&s_bar[warp * RING]);
+    // lane r copies one row of the group: r < LPV the raw plane r, LPV <= r < 2 LPV the dE0 plane r - LPV, r == 2 LPV the dT run
+    // (lanes r and r - LPV own chunk plane k = r % LPV themselves, so their own base pointers are the row's)
+    const bool row_raw = lane < LPV, row_de0 = lane >= LPV && lane < 2 * LPV && de0p != nullptr, row_dt = lane == 2 * LPV;
+    const uint32_t row_dst = row_raw ? (uint32_t)(lane * R::RS_RAW) : (row_dt ? (uint32_t)R::DT_OFF : (uint32_t)(R::DE0_OFF + (lane - LPV) * R::RS_DE0));
+    const uint32_t row_bytes = row_raw ? (uint32_t)(VPW * 16) : (row_dt ? (uint32_t)(VPW * 4) : (uint32_t)(VPW * R::GB));
+    const uint32_t group_bytes = (uint32_t)(LPV * VPW * 16 + VPW * 4) + (de0p ? (uint32_t)(LPV * VPW * R::GB) : 0u);
+    auto fill = [&](int slot, long long vb) {     // the whole warp calls it (converged)
+      const uint32_t bar = bar0 + 8u * (uint32_t)slot;
+      if (lane == 0) mbar_expect_tx(bar, group_bytes);
+      __syncwarp();
+      const uint32_t dst = ring0 + (uint32_t)(slot * R::STAGE) + row_dst;
+      if (row_raw) bulk_g2s(dst, rawp + (size_t)vb * 8, row_bytes, bar);
+      else if (row_de0) bulk_g2s(dst, de0p + (size_t)vb * 8, row_bytes, bar);
+      else if (row_dt) bulk_g2s(dst, dTp + vb, row_bytes, bar);
+    };
 #pragma unroll
-  for (int j = 0; j < PF; ++j)
-    if (vb0 + j * vstep < a.V) prefetch(pre[j], vb0 + j * vstep + vsub);
+    for (int j = 0; j < RING; ++j)
+      if (vb0 + j * vstep < a.V) fill(j, vb0 + j * vstep);
+    int slot = 0;
+    uint32_t phase = 0;
 #pragma unroll 1
-  for (long long vb = vb0; vb < a.V; vb += vstep) {
-    const Pre cur = pre[0];
+    for (long long vb = vb0; vb < a.V; vb += vstep) {
+      mbar_wait(bar0 + 8u * (uint32_t)slot, phase);
+      const uint32_t src = ring0 + (uint32_t)(slot * R::STAGE);
+      Pre cur;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(cur.raw.u[0]), "=r"(cur.raw.u[1]), "=r"(cur.raw.u[2]), "=r"(cur.raw.u[3])
+                   : "r"(src + (uint32_t)(k * R::RS_RAW + vsub * 16)));
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur.dT) : "r"(src + (uint32_t)(R::DT_OFF + vsub * 4)));
+      if (de0p) {
+        const uint32_t ga = src + (uint32_t)(R::DE0_OFF + k * R::RS_DE0 + vsub * R::GB);
+#ifdef SEUNET_GRAD_BF16
+        Chunk8 gc;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(gc.u[0]), "=r"(gc.u[1]), "=r"(gc.u[2]), "=r"(gc.u[3]) : "r"(ga));
+        chunk_to_floats_bf16(gc, cur.de0);
+#else
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cur.de0[0]), "=f"(cur.de0[1]), "=f"(cur.de0[2]), "=f"(cur.de0[3]) : "r"(ga));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cur.de0[4]), "=f"(cur.de0[5]), "=f"(cur.de0[6]), "=f"(cur.de0[7]) : "r"(ga + 16u));
+#endif
+      } else {
 #pragma unroll
-    for (int j = 0; j + 1 < PF; ++j) pre[j] = pre[j + 1];   // (13 register moves per ~200-instruction body)
-    if (vb + PF * vstep < a.V) prefetch(pre[PF - 1], vb + PF * vstep + vsub);
-    process(cur, vb + vsub);
+        for (int i = 0; i < 8; ++i) cur.de0[i] = 0.f;
+      }
+      process(cur, vb + vsub);
+      // refill the slot only after its values have been consumed (generic-proxy reads before the async-proxy write)
+      __syncwarp();
+      if (vb + RING * vstep < a.V) fill(slot, vb + RING * vstep);
+      if (++slot == RING) { slot = 0; phase ^= 1u; }
+    }
+  } else {
+    Pre pre[PF];
+#pragma unroll
+    for (int j = 0; j < PF; ++j)
+      if (vb0 + j * vstep < a.V) prefetch(pre[j], vb0 + j * vstep + vsub);
+#pragma unroll 1
+    for (long long vb = vb0; vb < a.V; vb += vstep) {
+      const Pre cur = pre[0];
+#pragma unroll
+      for (int j = 0; j + 1 < PF; ++j) pre[j] = pre[j + 1];   // (13 register moves per ~200-instruction body)
+      if (vb + PF * vstep < a.V) prefetch(pre[PF - 1], vb + PF * vstep + vsub);
+      process(cur, vb + vsub);
+    }
   }
   if (PASS == 2) return;
   // reduce over the voxel sub-lanes of the warp, then over warps, then one atomic per value per block
@@ -225,13 +301,28 @@ static int launch_sse_bwd_c(const SseBwdArgs& a, cudaStream_t st) {
   dim3 grid((unsigned)gx, a.N);
   // prefetch depth 2 only where the one-group-ahead version is short of bytes in flight (A/B, tools/r02_call50.sh)
   static const int pf_env = getenv("SEUNET_BWDA_PF") ? atoi(getenv("SEUNET_BWDA_PF")) : 0;
+  static const bool ring = !(getenv("SEUNET_BWDA_RING") && atoi(getenv("SEUNET_BWDA_RING")) == 0);   // A/B knob
   const bool deep = PASS == 0 && (pf_env ? pf_env == 2 : kSseBwdDeep<C>);
-  if (deep) {
-    if (a.wse2) sse_bwd_a_kernel<C, 2, 2, 0><<<grid, 256, 0, st>>>(a);
-    else sse_bwd_a_kernel<C, 1, 2, 0><<<grid, 256, 0, st>>>(a);
+  // bulk copies need 16-byte aligned sources (plan buffers always are; dT of level 0 is the caller's dpred tensor)
+  const bool aligned = ((((uintptr_t)a.raw) | ((uintptr_t)a.dE0) | ((uintptr_t)a.dT)) & 15u) == 0 && a.V % 32 == 0;
+  if (ring && !deep && aligned) {
+    constexpr int smem = 8 * kSseRingDepth * SseRing<C>::STAGE;
+    static bool attr_set[64] = {};   // per-device function attribute (see conv_launch_t)
+    int dev = 0;
+    SEUNET_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      SEUNET_CUDA_CHECK(cudaFuncSetAttribute(sse_bwd_a_kernel<C, 1, 1, PASS, kSseRingDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      SEUNET_CUDA_CHECK(cudaFuncSetAttribute(sse_bwd_a_kernel<C, 2, 1, PASS, kSseRingDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    if (a.wse2) sse_bwd_a_kernel<C, 2, 1, PASS, kSseRingDepth><<<grid, 256, smem, st>>>(a);
+    else sse_bwd_a_kernel<C, 1, 1, PASS, kSseRingDepth><<<grid, 256, smem, st>>>(a);
+  } else if (deep) {
+    if (a.wse2) sse_bwd_a_kernel<C, 2, 2, 0, 0><<<grid, 256, 0, st>>>(a);
+    else sse_bwd_a_kernel<C, 1, 2, 0, 0><<<grid, 256, 0, st>>>(a);
   } else {
-    if (a.wse2) sse_bwd_a_kernel<C, 2, 1, PASS><<<grid, 256, 0, st>>>(a);
-    else sse_bwd_a_kernel<C, 1, 1, PASS><<<grid, 256, 0, st>>>(a);
+    if (a.wse2) sse_bwd_a_kernel<C, 2, 1, PASS, 0><<<grid, 256, 0, st>>>(a);
+    else sse_bwd_a_kernel<C, 1, 1, PASS, 0><<<grid, 256, 0, st>>>(a);
   }
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
