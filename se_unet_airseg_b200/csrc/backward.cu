@@ -12,37 +12,31 @@ constexpr float kInEps = 1e-5f;
 __device__ __forceinline__ float lrelu_grad(float n) { return n > 0.f ? 1.f : 0.01f; }
 __device__ __forceinline__ void atomic_max_pos(unsigned int* p, float v) { atomicMax(p, __float_as_uint(v)); }
 
-// per-layer power-of-two pre-scaling of dY (the 16-bit operand of the tensor-core dgrad / wgrad), from max |dn * rstd|
-__device__ __forceinline__ float dy_scale_from_max(unsigned int bits) {
-  const float mx = __uint_as_float(bits);
-  if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
-  float e = 8.f - ceilf(log2f(mx));          // largest |dn*rstd| lands in [2^7, 2^8]
-  e = fminf(fmaxf(e, -100.f), 100.f);
-  return exp2f(e);
-}
-
 // =============================================================================================
-// SSE block backward.  PASS 0: pass A (gate / activation backward + per-(n,c) reductions) writing dn for the generic pass B
-// (norm_bwd_b_kernel).  PASS 1 / PASS 2 (round 2, late): the same pass A WITHOUT the dn store, and a pass B that RECOMPUTES dn
-// from the same inputs with the same instruction sequence and writes dY directly - dn never touches HBM: per element and
-// channel 6 B read in pass A' and 6 B read + 2 B written in pass B' instead of 6 + 4 and 6 + 2 (dn is fp32).
+// SSE block backward, pass A
 // =============================================================================================
-// RING > 0 (round 2, late): the inputs of a warp's next RING voxel groups are in flight as bulk copies (cp.async.bulk, one
-// mbarrier per warp and ring slot) into a warp-private shared-memory ring instead of as register prefetch: the kernel runs
-// at 25 % occupancy, so the bytes in flight per SM - 26 KB with one group ahead in registers, which by Little's law caps the
-// read rate near 3 TB/s; two groups ahead spill - decide the bandwidth, and a ring slot costs no registers.
+// RING > 0 (round 2, late): the inputs of a warp's next RING voxel spans travel as bulk copies (cp.async.bulk, one mbarrier
+// per warp and ring slot) into a warp-private shared-memory ring instead of as register prefetch.  ncu on the register
+// version: 25 % occupancy (128 registers), a third of all stall samples on the first use of the prefetched chunk (long
+// scoreboard) - 26 KB in flight per SM cap the read rate near 3 TB/s and a second group in registers spills.  A ring slot
+// costs no registers.  One ELECTED lane issues the copies with warp-uniform addresses (the first ring version let 2 LPV + 1
+// lanes issue one row each: UBLKCP takes uniform registers, so ptxas serialised the lanes in a waterfall loop, +45 % warp
+// instructions, and the kernel got slower although the long-scoreboard stalls were gone); a slot holds a SPAN of 1-2 voxel
+// groups so that a row is >= 128 B and there are half as many copies.
 template <int C> struct SseRing {
   static constexpr int LPV = C / 8, VPW = 32 / LPV;
+  static constexpr int SPAN = C >= 32 ? 2 : 1;                // voxel groups per slot
+  static constexpr int SVX = SPAN * VPW;                      // voxels per slot
   static constexpr int GB = 8 * (int)sizeof(grad_t);          // bytes of one gradient chunk
-  static constexpr int RS_RAW = VPW * 16 + 16;                // row (one chunk plane, VPW voxels) + 16 B against bank conflicts
-  static constexpr int RS_DE0 = VPW * GB + 16;
+  static constexpr int RS_RAW = SVX * 16 + 128 / LPV;         // row = one chunk plane of the span; the pad spreads the LPV rows over the banks
+  static constexpr int RS_DE0 = SVX * GB + 16;
   static constexpr int DE0_OFF = LPV * RS_RAW;
   static constexpr int DT_OFF = DE0_OFF + LPV * RS_DE0;
-  static constexpr int STAGE = (DT_OFF + 128 + 127) / 128 * 128;
+  static constexpr int STAGE = (DT_OFF + SVX * 4 + 127) / 128 * 128;
 };
-constexpr int kSseRingDepth = 4;
+constexpr int kSseRingDepth = 3;
 
-template <int C, int GATES, int PF, int PASS, int RING>
+template <int C, int GATES, int PF, int RING>
 __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant__ SseBwdArgs a) {
   constexpr int LPV = C / 8;     // lanes cooperating on one voxel (one 8-channel chunk each)
   constexpr int VPW = 32 / LPV;  // voxels per warp
@@ -50,24 +44,12 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
   __shared__ __align__(8) unsigned long long s_bar[8 * (RING > 0 ? RING : 1)];
   if (RING > 0) {
     if (threadIdx.x < 8 * RING) mbar_init(smem_u32(&s_bar[threadIdx.x]), 1);
-    fence_mbar_init();
+    fence_mbar_init();        // (the __syncthreads() after the statistics prologue publishes the barriers)
   }
   __shared__ float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
-  __shared__ float s_red[PASS == 2 ? 1 : 8][5][C];
+  __shared__ float s_red[8][5][C];
   __shared__ float s_cst[8], s_max[8];
-  __shared__ float s_m1[PASS == 2 ? C : 1], s_m2[PASS == 2 ? C : 1], s_scale;
   const int n = blockIdx.y;
-  if (PASS == 2) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      s_m1[c] = (float)(a.redS[((size_t)n * 64 + c) * 2] / (double)a.V);
-      s_m2[c] = (float)(a.redS[((size_t)n * 64 + c) * 2 + 1] / (double)a.V);
-    }
-    if (threadIdx.x == 255) {
-      const float sc = dy_scale_from_max(*a.dymax);
-      s_scale = sc;
-      if (blockIdx.x == 0 && n == 0) { a.scale_out[0] = sc; a.scale_out[1] = 1.f / sc; }
-    }
-  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const double s = a.stats[((size_t)n * a.stats_c + c) * 2], q = a.stats[((size_t)n * a.stats_c + c) * 2 + 1];
     const double mean = s / (double)a.V;
@@ -80,7 +62,8 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
     s_weff[c] = a.weff[(size_t)n * 64 + c];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform (bulk-copy addresses live in uniform registers)
   const int k = lane % LPV, vsub = lane / LPV;
   float S1[8], S2[8], Wse[8], Wse2[8], Weff[8], cst = 0.f, mx = 0.f;
 #pragma unroll
@@ -158,83 +141,83 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
       const int c = k * 8 + i;
       const float da = fmaf(s_wse[c], k1, da1[i] * g1);
       dn[i] = da * lrelu_grad(nn[i]);
-      if (PASS != 2) {
-        S1[i] += dn[i];
-        S2[i] = fmaf(dn[i], nn[i], S2[i]);
-        Wse[i] = fmaf(k1, av[i], Wse[i]);
-        Wse2[i] = fmaf(k2, a1[i], Wse2[i]);
-        Weff[i] = fmaf(dT, e0[i], Weff[i]);
-        mx = fmaxf(mx, fabsf(dn[i] * s_rstd[c]));
-      }
+      S1[i] += dn[i];
+      S2[i] = fmaf(dn[i], nn[i], S2[i]);
+      Wse[i] = fmaf(k1, av[i], Wse[i]);
+      Wse2[i] = fmaf(k2, a1[i], Wse2[i]);
+      Weff[i] = fmaf(dT, e0[i], Weff[i]);
+      mx = fmaxf(mx, fabsf(dn[i] * s_rstd[c]));
     }
-    if (PASS == 0) st_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
-    if (PASS == 2) {   // InstanceNorm backward on the recomputed dn (same arithmetic as norm_bwd_b_kernel)
-      const float sc = s_scale;
-      float dy[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = k * 8 + i;
-        const float t = s_rstd[c] * (dn[i] - s_m1[c] - nn[i] * s_m2[c]) * sc;
-        dy[i] = fminf(fmaxf(t, -60000.f), 60000.f);
-      }
-      st_chunk(a.dy + (((size_t)n * a.dy_chunks + k) * a.V + v) * 8, floats_to_chunk(dy));
-    } else if (k == 0) cst += dT;
+    if (k == 0) cst += dT;
+    st_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
   };
   // V is a multiple of 32, so the whole warp is in range whenever its first voxel is
-  const long long vb0 = ((long long)blockIdx.x * 8 + warp) * VPW;
   if constexpr (RING > 0) {
     using R = SseRing<C>;
     const uint32_t ring0 = smem_u32(s_ring) + (uint32_t)(warp * RING * R::STAGE);
     const uint32_t bar0 = smem_u32(&s_bar[warp * RING]);
-    // lane r copies one row of the group: r < LPV the raw plane r, LPV <= r < 2 LPV the dE0 plane r - LPV, r == 2 LPV the dT run
-    // (lanes r and r - LPV own chunk plane k = r % LPV themselves, so their own base pointers are the row's)
-    const bool row_raw = lane < LPV, row_de0 = lane >= LPV && lane < 2 * LPV && de0p != nullptr, row_dt = lane == 2 * LPV;
-    const uint32_t row_dst = row_raw ? (uint32_t)(lane * R::RS_RAW) : (row_dt ? (uint32_t)R::DT_OFF : (uint32_t)(R::DE0_OFF + (lane - LPV) * R::RS_DE0));
-    const uint32_t row_bytes = row_raw ? (uint32_t)(VPW * 16) : (row_dt ? (uint32_t)(VPW * 4) : (uint32_t)(VPW * R::GB));
-    const uint32_t group_bytes = (uint32_t)(LPV * VPW * 16 + VPW * 4) + (de0p ? (uint32_t)(LPV * VPW * R::GB) : 0u);
-    auto fill = [&](int slot, long long vb) {     // the whole warp calls it (converged)
-      const uint32_t bar = bar0 + 8u * (uint32_t)slot;
-      if (lane == 0) mbar_expect_tx(bar, group_bytes);
+    const long long sstep = (long long)gridDim.x * 8 * R::SVX;
+    const long long vs0 = ((long long)blockIdx.x * 8 + warp) * R::SVX;
+    const act_t* raw_n = a.raw + (size_t)n * a.raw_chunks * a.V * 8;                                   // chunk plane 0 of the sample
+    const grad_t* de0_n = a.dE0 ? a.dE0 + ((size_t)n * a.dE0_chunks + a.dE0_off) * a.V * 8 : nullptr;
+    const uint32_t span_bytes = (uint32_t)(LPV * R::SVX * 16 + R::SVX * 4) + (de0_n ? (uint32_t)(LPV * R::SVX * R::GB) : 0u);
+    auto fill = [&](int slot, long long vs) {     // whole warp, converged; one elected lane issues the 2 LPV + 1 row copies
+      if (elect_one_sync()) {
+        const uint32_t bar = bar0 + 8u * (uint32_t)slot;
+        const uint32_t dst = ring0 + (uint32_t)(slot * R::STAGE);
+        mbar_expect_tx(bar, span_bytes);
+        const act_t* rp = raw_n + (size_t)vs * 8;
+#pragma unroll
+        for (int kk = 0; kk < LPV; ++kk) bulk_g2s(dst + (uint32_t)(kk * R::RS_RAW), rp + (size_t)kk * a.V * 8, (uint32_t)(R::SVX * 16), bar);
+        if (de0_n) {
+          const grad_t* gp = de0_n + (size_t)vs * 8;
+#pragma unroll
+          for (int kk = 0; kk < LPV; ++kk)
+            bulk_g2s(dst + (uint32_t)(R::DE0_OFF + kk * R::RS_DE0), gp + (size_t)kk * a.V * 8, (uint32_t)(R::SVX * R::GB), bar);
+        }
+        bulk_g2s(dst + (uint32_t)R::DT_OFF, dTp + vs, (uint32_t)(R::SVX * 4), bar);
+      }
       __syncwarp();
-      const uint32_t dst = ring0 + (uint32_t)(slot * R::STAGE) + row_dst;
-      if (row_raw) bulk_g2s(dst, rawp + (size_t)vb * 8, row_bytes, bar);
-      else if (row_de0) bulk_g2s(dst, de0p + (size_t)vb * 8, row_bytes, bar);
-      else if (row_dt) bulk_g2s(dst, dTp + vb, row_bytes, bar);
     };
 #pragma unroll
     for (int j = 0; j < RING; ++j)
-      if (vb0 + j * vstep < a.V) fill(j, vb0 + j * vstep);
+      if (vs0 + j * sstep < a.V) fill(j, vs0 + j * sstep);
     int slot = 0;
     uint32_t phase = 0;
 #pragma unroll 1
-    for (long long vb = vb0; vb < a.V; vb += vstep) {
+    for (long long vs = vs0; vs < a.V; vs += sstep) {
       mbar_wait(bar0 + 8u * (uint32_t)slot, phase);
       const uint32_t src = ring0 + (uint32_t)(slot * R::STAGE);
-      Pre cur;
-      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(cur.raw.u[0]), "=r"(cur.raw.u[1]), "=r"(cur.raw.u[2]), "=r"(cur.raw.u[3])
-                   : "r"(src + (uint32_t)(k * R::RS_RAW + vsub * 16)));
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur.dT) : "r"(src + (uint32_t)(R::DT_OFF + vsub * 4)));
-      if (de0p) {
-        const uint32_t ga = src + (uint32_t)(R::DE0_OFF + k * R::RS_DE0 + vsub * R::GB);
-#ifdef SEUNET_GRAD_BF16
-        Chunk8 gc;
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(gc.u[0]), "=r"(gc.u[1]), "=r"(gc.u[2]), "=r"(gc.u[3]) : "r"(ga));
-        chunk_to_floats_bf16(gc, cur.de0);
-#else
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cur.de0[0]), "=f"(cur.de0[1]), "=f"(cur.de0[2]), "=f"(cur.de0[3]) : "r"(ga));
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cur.de0[4]), "=f"(cur.de0[5]), "=f"(cur.de0[6]), "=f"(cur.de0[7]) : "r"(ga + 16u));
-#endif
-      } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) cur.de0[i] = 0.f;
+      for (int s = 0; s < R::SPAN; ++s) {
+        const int vl = s * VPW + vsub;      // voxel inside the span
+        Pre cur;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(cur.raw.u[0]), "=r"(cur.raw.u[1]), "=r"(cur.raw.u[2]), "=r"(cur.raw.u[3])
+                     : "r"(src + (uint32_t)(k * R::RS_RAW + vl * 16)));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cur.dT) : "r"(src + (uint32_t)(R::DT_OFF + vl * 4)));
+        if (de0_n) {
+          const uint32_t ga = src + (uint32_t)(R::DE0_OFF + k * R::RS_DE0 + vl * R::GB);
+#ifdef SEUNET_GRAD_BF16
+          Chunk8 gc;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(gc.u[0]), "=r"(gc.u[1]), "=r"(gc.u[2]), "=r"(gc.u[3]) : "r"(ga));
+          chunk_to_floats_bf16(gc, cur.de0);
+#else
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cur.de0[0]), "=f"(cur.de0[1]), "=f"(cur.de0[2]), "=f"(cur.de0[3]) : "r"(ga));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cur.de0[4]), "=f"(cur.de0[5]), "=f"(cur.de0[6]), "=f"(cur.de0[7]) : "r"(ga + 16u));
+#endif
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cur.de0[i] = 0.f;
+        }
+        process(cur, vs + vl);
       }
-      process(cur, vb + vsub);
       // refill the slot only after its values have been consumed (generic-proxy reads before the async-proxy write)
       __syncwarp();
-      if (vb + RING * vstep < a.V) fill(slot, vb + RING * vstep);
+      if (vs + RING * sstep < a.V) fill(slot, vs + RING * sstep);
       if (++slot == RING) { slot = 0; phase ^= 1u; }
     }
   } else {
+    const long long vb0 = ((long long)blockIdx.x * 8 + warp) * VPW;
     Pre pre[PF];
 #pragma unroll
     for (int j = 0; j < PF; ++j)
@@ -248,7 +231,6 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
       process(cur, vb + vsub);
     }
   }
-  if (PASS == 2) return;
   // reduce over the voxel sub-lanes of the warp, then over warps, then one atomic per value per block
   auto wreduce = [&](float v) {
 #pragma unroll
@@ -288,66 +270,66 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
 
 template <int C> constexpr bool kSseBwdDeep = false;   // measured: depth 2 spills (128 registers) and is 10-30 % slower
 
-template <int C, int PASS>
-static int launch_sse_bwd_c(const SseBwdArgs& a, cudaStream_t st) {
-  constexpr int VPB = 8 * (32 / (C / 8));
+template <int C>
+static int launch_sse_bwd_a_c(const SseBwdArgs& a, cudaStream_t st) {
+  static const bool ring_env = !(getenv("SEUNET_BWDA_RING") && atoi(getenv("SEUNET_BWDA_RING")) == 0);   // A/B knob
+  static const int pf_env = getenv("SEUNET_BWDA_PF") ? atoi(getenv("SEUNET_BWDA_PF")) : 0;
+  const bool deep = pf_env ? pf_env == 2 : kSseBwdDeep<C>;
+  // bulk copies need 16-byte aligned sources (plan buffers always are; dT of level 0 is the caller's dpred tensor)
+  const bool aligned = ((((uintptr_t)a.raw) | ((uintptr_t)a.dE0) | ((uintptr_t)a.dT)) & 15u) == 0 && a.V % 32 == 0;
+  const bool ring = ring_env && !deep && aligned;
+  const int VPB = 8 * (ring ? SseRing<C>::SVX : 32 / (C / 8));   // voxels per block and loop iteration
   const long long need = (a.V + VPB - 1) / VPB;
   // Every block ends with 5*C same-address atomics per sample: at the coarse levels (few voxels) thousands of one-iteration
   // blocks spent their time in that tail and in the per-block statistics prologue.  Give each warp >= 16 voxel groups, but
   // keep >= 4 blocks per SM in flight over the whole batch.
-  static const int floor_per_sm = getenv("SEUNET_BWDA_FLOOR") ? std::max(1, atoi(getenv("SEUNET_BWDA_FLOOR"))) : 4;   // A/B knob
-  const long long floor_blocks = (148 * floor_per_sm + a.N - 1) / a.N;
+  const long long floor_blocks = (148 * 4 + a.N - 1) / a.N;
   const long long gx = std::min<long long>(need, std::max<long long>(floor_blocks, std::min<long long>(148 * 8, need / 16)));
   dim3 grid((unsigned)gx, a.N);
-  // prefetch depth 2 only where the one-group-ahead version is short of bytes in flight (A/B, tools/r02_call50.sh)
-  static const int pf_env = getenv("SEUNET_BWDA_PF") ? atoi(getenv("SEUNET_BWDA_PF")) : 0;
-  static const bool ring = !(getenv("SEUNET_BWDA_RING") && atoi(getenv("SEUNET_BWDA_RING")) == 0);   // A/B knob
-  const bool deep = PASS == 0 && (pf_env ? pf_env == 2 : kSseBwdDeep<C>);
-  // bulk copies need 16-byte aligned sources (plan buffers always are; dT of level 0 is the caller's dpred tensor)
-  const bool aligned = ((((uintptr_t)a.raw) | ((uintptr_t)a.dE0) | ((uintptr_t)a.dT)) & 15u) == 0 && a.V % 32 == 0;
-  if (ring && !deep && aligned) {
+  if (ring) {
     constexpr int smem = 8 * kSseRingDepth * SseRing<C>::STAGE;
     static bool attr_set[64] = {};   // per-device function attribute (see conv_launch_t)
     int dev = 0;
     SEUNET_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-      SEUNET_CUDA_CHECK(cudaFuncSetAttribute(sse_bwd_a_kernel<C, 1, 1, PASS, kSseRingDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      SEUNET_CUDA_CHECK(cudaFuncSetAttribute(sse_bwd_a_kernel<C, 2, 1, PASS, kSseRingDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      SEUNET_CUDA_CHECK(cudaFuncSetAttribute(sse_bwd_a_kernel<C, 1, 1, kSseRingDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      SEUNET_CUDA_CHECK(cudaFuncSetAttribute(sse_bwd_a_kernel<C, 2, 1, kSseRingDepth>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    if (a.wse2) sse_bwd_a_kernel<C, 2, 1, PASS, kSseRingDepth><<<grid, 256, smem, st>>>(a);
-    else sse_bwd_a_kernel<C, 1, 1, PASS, kSseRingDepth><<<grid, 256, smem, st>>>(a);
-  } else if (deep) {
-    if (a.wse2) sse_bwd_a_kernel<C, 2, 2, 0, 0><<<grid, 256, 0, st>>>(a);
-    else sse_bwd_a_kernel<C, 1, 2, 0, 0><<<grid, 256, 0, st>>>(a);
+    if (a.wse2) sse_bwd_a_kernel<C, 2, 1, kSseRingDepth><<<grid, 256, smem, st>>>(a);
+    else sse_bwd_a_kernel<C, 1, 1, kSseRingDepth><<<grid, 256, smem, st>>>(a);
+  } else if (deep) {   // register prefetch two groups ahead (A/B, tools/r02_call50.sh: spills, slower)
+    if (a.wse2) sse_bwd_a_kernel<C, 2, 2, 0><<<grid, 256, 0, st>>>(a);
+    else sse_bwd_a_kernel<C, 1, 2, 0><<<grid, 256, 0, st>>>(a);
   } else {
-    if (a.wse2) sse_bwd_a_kernel<C, 2, 1, PASS, 0><<<grid, 256, 0, st>>>(a);
-    else sse_bwd_a_kernel<C, 1, 1, PASS, 0><<<grid, 256, 0, st>>>(a);
+    if (a.wse2) sse_bwd_a_kernel<C, 2, 1, 0><<<grid, 256, 0, st>>>(a);
+    else sse_bwd_a_kernel<C, 1, 1, 0><<<grid, 256, 0, st>>>(a);
   }
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
-template <int C>
-static int launch_sse_bwd_p(const SseBwdArgs& a, int pass, cudaStream_t st) {
-  if (pass == 0) return launch_sse_bwd_c<C, 0>(a, st);
-  if (pass == 1) return launch_sse_bwd_c<C, 1>(a, st);
-  if (!a.dy || !a.scale_out) { seunet_set_error("sse_bwd: pass B needs dy and scale_out"); return 1; }
-  return launch_sse_bwd_c<C, 2>(a, st);
-}
-int launch_sse_bwd(int C, const SseBwdArgs& a, int pass, cudaStream_t st) {
+int launch_sse_bwd_a(int C, const SseBwdArgs& a, cudaStream_t st) {
   switch (C) {
-    case 8: return launch_sse_bwd_p<8>(a, pass, st);
-    case 16: return launch_sse_bwd_p<16>(a, pass, st);
-    case 32: return launch_sse_bwd_p<32>(a, pass, st);
-    case 64: return launch_sse_bwd_p<64>(a, pass, st);
+    case 8: return launch_sse_bwd_a_c<8>(a, st);
+    case 16: return launch_sse_bwd_a_c<16>(a, st);
+    case 32: return launch_sse_bwd_a_c<32>(a, st);
+    case 64: return launch_sse_bwd_a_c<64>(a, st);
   }
-  seunet_set_error("sse_bwd: C=%d unsupported", C);
+  seunet_set_error("sse_bwd_a: C=%d unsupported", C);
   return 1;
 }
 
 // =============================================================================================
 // InstanceNorm backward, pass B (shared by SSE and CAT blocks)
 // =============================================================================================
+__device__ __forceinline__ float dy_scale_from_max(unsigned int bits) {
+  const float mx = __uint_as_float(bits);
+  if (!(mx > 0.f) || !isfinite(mx)) return 1.f;
+  float e = 8.f - ceilf(log2f(mx));          // largest |dn*rstd| lands in [2^7, 2^8]
+  e = fminf(fmaxf(e, -100.f), 100.f);
+  return exp2f(e);
+}
+
 __global__ void __launch_bounds__(256) norm_bwd_b_kernel(const __grid_constant__ NormBwdArgs a) {
   __shared__ float s_mean[8], s_rstd[8], s_m1[8], s_m2[8];
   __shared__ float s_scale;

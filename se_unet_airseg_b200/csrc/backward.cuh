@@ -32,13 +32,8 @@ struct SseBwdArgs {
   float* dwse; float* dwse2;                        // [64] each (summed over n)
   float* dweff; float* dcst;                        // [N][64], [N]
   unsigned int* dymax;                              // max |dn * rstd| as float bits
-  // pass B by recomputation (pass == 2) only
-  act_t* dy; int dy_chunks;                         // [n][dy_chunks][V][8], pre-scaled by 2^s
-  float* scale_out;                                 // [2]: scale, 1/scale (written by block 0)
 };
-// pass 0: pass A that stores dn (for launch_norm_bwd_b); pass 1: pass A, reductions only; pass 2: pass B recomputing dn (after
-// pass 1 of the same layer has completed: reads redS and dymax)
-int launch_sse_bwd(int C, const SseBwdArgs& a, int pass, cudaStream_t st);
+int launch_sse_bwd_a(int C, const SseBwdArgs& a, cudaStream_t st);
 
 struct NormBwdArgs {          // pass B: dy = rstd * (dn - mean(dn) - n * mean(dn*n)) * 2^s
   const act_t* raw; int raw_chunks;

@@ -1,8 +1,7 @@
-"""The backward schedule's environment knobs must not change the result: shallow data-gradient tiles, the side-stream
-head adjoint and the bulk-copy input ring of pass A are bit-identical re-schedulings (same arithmetic, same per-voxel
-accumulation order), the recomputing pass B of the SSE blocks
-(SEUNET_BWD_RECOMPUTE=1) re-evaluates dn with the same instruction sequence and may only differ by the fp32 contraction of
-the final dY expression.  The knobs are read once per process, so each setting runs tools/grad_dump.py in its own process."""
+"""The backward schedule's environment knobs must not change the result: shallow data-gradient tiles and the side-stream head
+adjoint are bit-identical re-schedulings (same arithmetic, same per-voxel accumulation order); the bulk-copy input ring of
+pass A maps voxels to threads differently, which only reorders fp32 partial sums of the per-channel reductions.  The knobs
+are read once per process, so each setting runs tools/grad_dump.py in its own process."""
 import os
 import subprocess
 import sys
@@ -28,7 +27,6 @@ def test_backward_knobs_do_not_change_the_gradient(tmp_path, B, S):
     base = _dump(tmp_path, "base", {"SEUNET_CONV_SHALLOW": "0", "SEUNET_BWD_HEAD_SIDE": "0", "SEUNET_BWD_CONC_VOX": "0",
                                     "SEUNET_BWDA_RING": "0"}, B, S)
     dflt = _dump(tmp_path, "default", {}, B, S)
-    reco = _dump(tmp_path, "recompute", {"SEUNET_BWD_RECOMPUTE": "1"}, B, S)
     gn = base["grads"].norm().item()
     assert gn > 0 and bool(torch.isfinite(base["grads"]).all())
     # default schedule (shallow tiles, side streams) vs the fully serial one: the weight-gradient partials are reduced in a fixed
@@ -36,4 +34,3 @@ def test_backward_knobs_do_not_change_the_gradient(tmp_path, B, S):
     # sums may differ - the run-to-run noise of one and the same schedule (tools/soak.py: 4e-7)
     assert (dflt["grads"] - base["grads"]).norm().item() <= 5e-6 * gn
     assert abs(dflt["loss"].item() - base["loss"].item()) <= 1e-6
-    assert (reco["grads"] - dflt["grads"]).norm().item() <= 1e-4 * gn
