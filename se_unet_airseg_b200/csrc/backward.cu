@@ -83,6 +83,13 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
   const float* dTp = a.dT + (size_t)n * a.V;
   struct Pre { Chunk8 raw; float de0[8]; float dT; };
   auto prefetch = [&](Pre& p, long long v) {
+    if (v >= a.V) {   // tail of a level whose voxel count is not a multiple of the warp's group (coarsest level of ragged shapes)
+      p.raw.u[0] = p.raw.u[1] = p.raw.u[2] = p.raw.u[3] = 0u;
+      p.dT = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) p.de0[i] = 0.f;
+      return;
+    }
     p.raw = ld_chunk_stream(rawp + (size_t)v * 8);
     p.dT = dTp[v];
     if (de0p) ld_grad8(de0p + (size_t)v * 8, p.de0);
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
       for (int i = 0; i < 8; ++i) p.de0[i] = 0.f;
     }
   };
-  auto process = [&](const Pre& p, long long v) {
+  auto process = [&](const Pre& p, long long v, const bool live) {   // live: v < V (the lanes of a dead voxel only feed each other)
     float f[8], nn[8], av[8], e0[8], de0[8];
     chunk_to_floats(p.raw, f);
     const float dT = p.dT;
@@ -141,17 +148,20 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
       const int c = k * 8 + i;
       const float da = fmaf(s_wse[c], k1, da1[i] * g1);
       dn[i] = da * lrelu_grad(nn[i]);
-      S1[i] += dn[i];
-      S2[i] = fmaf(dn[i], nn[i], S2[i]);
-      Wse[i] = fmaf(k1, av[i], Wse[i]);
-      Wse2[i] = fmaf(k2, a1[i], Wse2[i]);
-      Weff[i] = fmaf(dT, e0[i], Weff[i]);
-      mx = fmaxf(mx, fabsf(dn[i] * s_rstd[c]));
+      if (live) {
+        S1[i] += dn[i];
+        S2[i] = fmaf(dn[i], nn[i], S2[i]);
+        Wse[i] = fmaf(k1, av[i], Wse[i]);
+        Wse2[i] = fmaf(k2, a1[i], Wse2[i]);
+        Weff[i] = fmaf(dT, e0[i], Weff[i]);
+        mx = fmaxf(mx, fabsf(dn[i] * s_rstd[c]));
+      }
     }
-    if (k == 0) cst += dT;
-    st_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
+    if (live) {
+      if (k == 0) cst += dT;
+      st_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
+    }
   };
-  // V is a multiple of 32, so the whole warp is in range whenever its first voxel is
   if constexpr (RING > 0) {
     using R = SseRing<C>;
     const uint32_t ring0 = smem_u32(s_ring) + (uint32_t)(warp * RING * R::STAGE);
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
 #pragma unroll
           for (int i = 0; i < 8; ++i) cur.de0[i] = 0.f;
         }
-        process(cur, vs + vl);
+        process(cur, vs + vl, true);      // the ring path is only launched when V is a multiple of 32 (whole spans)
       }
       // refill the slot only after its values have been consumed (generic-proxy reads before the async-proxy write)
       __syncwarp();
@@ -228,7 +238,7 @@ __global__ void __launch_bounds__(256, 2) sse_bwd_a_kernel(const __grid_constant
 #pragma unroll
       for (int j = 0; j + 1 < PF; ++j) pre[j] = pre[j + 1];   // (13 register moves per ~200-instruction body)
       if (vb + PF * vstep < a.V) prefetch(pre[PF - 1], vb + PF * vstep + vsub);
-      process(cur, vb + vsub);
+      process(cur, vb + vsub, vb + vsub < a.V);
     }
   }
   // reduce over the voxel sub-lanes of the warp, then over warps, then one atomic per value per block
