@@ -241,12 +241,10 @@ template <int C> struct SseVpt { static constexpr int value = C <= 16 ? 4 : 1; }
 // registers (four resident blocks instead of three, no spill), half the serial arithmetic per thread and twice the threads
 // on the 32^3 / 16^3 levels, where the one-thread-per-voxel version was latency-bound (ncu: 19 us for 59 MB, 34 % of the
 // warp slots).  The gate sums and the folded side-branch sum are completed with one shuffle each.
-template <int C, int GATES, int SPLIT>
+template <int C, int GATES, int SPLIT, int VPT>
 __global__ void __launch_bounds__(256, SPLIT == 2 ? 4 : (C == 64 ? 3 : (C == 32 ? 4 : 6))) apply_sse_kernel(const __grid_constant__ SseArgs a) {
-  constexpr int VPT = SseVpt<C>::value;
   constexpr int KPT = C / 8 / SPLIT;       // channel chunks per thread
   constexpr int CT = C / SPLIT;            // channels per thread
-  static_assert(SPLIT == 1 || VPT == 1, "split variant: one voxel per thread pair");
   __shared__ __align__(16) float s_mean[C], s_rstd[C], s_wse[C], s_wse2[C], s_weff[C];
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -329,24 +327,33 @@ __global__ void __launch_bounds__(256, SPLIT == 2 ? 4 : (C == 64 ? 3 : (C == 32 
   }
 }
 
+template <int C, int SPLIT, int VPT>
+static int launch_apply_sse_v(int N, const SseArgs& a, cudaStream_t st) {
+  constexpr int VPB = 256 / SPLIT * VPT;
+  dim3 grid((unsigned)((a.V + VPB - 1) / VPB), N);
+  if (a.wse2) apply_sse_kernel<C, 2, SPLIT, VPT><<<grid, 256, 0, st>>>(a);
+  else apply_sse_kernel<C, 1, SPLIT, VPT><<<grid, 256, 0, st>>>(a);
+  SEUNET_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 template <int C>
 static int launch_apply_sse_c(int N, const SseArgs& a, cudaStream_t st) {
   static const int split_mask = getenv("SEUNET_SSE_SPLIT") ? atoi(getenv("SEUNET_SSE_SPLIT")) : kSseSplitDefault;   // bit 0: C = 64, bit 1: C = 32
   if constexpr (C >= 32) {
-    if (a.inference && (split_mask & (C == 64 ? 1 : 2))) {
-      dim3 grid((unsigned)((a.V + 127) / 128), N);
-      if (a.wse2) apply_sse_kernel<C, 2, 2><<<grid, 256, 0, st>>>(a);
-      else apply_sse_kernel<C, 1, 2><<<grid, 256, 0, st>>>(a);
-      SEUNET_CUDA_CHECK(cudaGetLastError());
-      return 0;
-    }
+    // Voxels per thread of the wide instances: with one voxel per thread every 128/256 voxels pay the block's fp64 statistics
+    // prologue and barrier, which is as long as the payload; looping over 4 voxel groups amortises it (dc5 48.9 -> 44.0 us per
+    // window, ec6 16.8 -> 14.6) - but only where enough blocks remain to fill the SMs (the 32^3 / 16^3 levels got slower).
+    // Per voxel the arithmetic is unchanged (8 groups per thread: no further gain).  SEUNET_SSE_VPT = 1 | 4: A/B knob.
+    static const int vpt_env = getenv("SEUNET_SSE_VPT") ? atoi(getenv("SEUNET_SSE_VPT")) : 4;
+    const bool split = a.inference && (split_mask & (C == 64 ? 1 : 2));
+    const long long groups = (long long)N * ((a.V + (split ? 127 : 255)) / (split ? 128 : 256));
+    const bool many = vpt_env >= 4 && groups / 4 >= 148 * 8;
+    if (split) return many ? launch_apply_sse_v<C, 2, 4>(N, a, st) : launch_apply_sse_v<C, 2, 1>(N, a, st);
+    return many ? launch_apply_sse_v<C, 1, 4>(N, a, st) : launch_apply_sse_v<C, 1, 1>(N, a, st);
+  } else {
+    return launch_apply_sse_v<C, 1, SseVpt<C>::value>(N, a, st);   // (8 voxels per thread measured: no further gain)
   }
-  constexpr int VPB = 256 * SseVpt<C>::value;
-  dim3 grid((unsigned)((a.V + VPB - 1) / VPB), N);
-  if (a.wse2) apply_sse_kernel<C, 2, 1><<<grid, 256, 0, st>>>(a);
-  else apply_sse_kernel<C, 1, 1><<<grid, 256, 0, st>>>(a);
-  SEUNET_CUDA_CHECK(cudaGetLastError());
-  return 0;
 }
 int launch_apply_sse(int C, int N, const SseArgs& a, cudaStream_t st) {
   switch (C) {
