@@ -340,6 +340,10 @@ __device__ __forceinline__ float dy_scale_from_max(unsigned int bits) {
   return exp2f(e);
 }
 
+// VPT voxel groups per block (rolled loop): the fp64 prologue + barrier of a block is as long as one load/store round trip, so
+// where enough blocks remain it is paid once per four groups (same finding as apply_sse in pointwise.cu): pass B total
+// 4.87 -> 3.80 ms at 8 x 128^3 (tools/r02_call72.sh); eight or sixteen groups per block: no further gain.
+template <int VPT>
 __global__ void __launch_bounds__(256) norm_bwd_b_kernel(const __grid_constant__ NormBwdArgs a) {
   __shared__ float s_mean[8], s_rstd[8], s_m1[8], s_m2[8];
   __shared__ float s_scale;
@@ -361,24 +365,34 @@ __global__ void __launch_bounds__(256) norm_bwd_b_kernel(const __grid_constant__
     if (blockIdx.x == 0 && k == 0 && n == 0) { a.scale_out[0] = sc; a.scale_out[1] = 1.f / sc; }
   }
   __syncthreads();
-  const long long v = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (v >= a.V) return;
-  float f[8], dn[8], dy[8];
-  chunk_to_floats(ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8), f);
-  ld_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
   const float sc = s_scale;
+#pragma unroll 1
+  for (int u = 0; u < VPT; ++u) {
+    const long long v = ((long long)blockIdx.x * VPT + u) * blockDim.x + threadIdx.x;
+    if (v >= a.V) return;
+    float f[8], dn[8], dy[8];
+    chunk_to_floats(ld_chunk_stream(a.raw + (((size_t)n * a.raw_chunks + k) * a.V + v) * 8), f);
+    ld_grad8(a.dn + (((size_t)n * a.dn_chunks + k) * a.V + v) * 8, dn);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float nn = (f[i] - s_mean[i]) * s_rstd[i];
-    float t = s_rstd[i] * (dn[i] - s_m1[i] - nn * s_m2[i]) * sc;
-    dy[i] = fminf(fmaxf(t, -60000.f), 60000.f);
+    for (int i = 0; i < 8; ++i) {
+      const float nn = (f[i] - s_mean[i]) * s_rstd[i];
+      float t = s_rstd[i] * (dn[i] - s_m1[i] - nn * s_m2[i]) * sc;
+      dy[i] = fminf(fmaxf(t, -60000.f), 60000.f);
+    }
+    st_chunk(a.dy + (((size_t)n * a.dy_chunks + k) * a.V + v) * 8, floats_to_chunk(dy));
   }
-  st_chunk(a.dy + (((size_t)n * a.dy_chunks + k) * a.V + v) * 8, floats_to_chunk(dy));
 }
 
 int launch_norm_bwd_b(const NormBwdArgs& a, cudaStream_t st) {
-  dim3 grid((unsigned)((a.V + 255) / 256), a.C / 8, a.N);
-  norm_bwd_b_kernel<<<grid, 256, 0, st>>>(a);
+  static const int vpt_env = getenv("SEUNET_BWDB_VPT") ? atoi(getenv("SEUNET_BWDB_VPT")) : 4;   // A/B knob
+  const long long groups = (a.V + 255) / 256;
+  if (vpt_env >= 4 && groups / 4 * (a.C / 8) * a.N >= 148 * 8) {
+    dim3 grid((unsigned)((groups + 3) / 4), a.C / 8, a.N);
+    norm_bwd_b_kernel<4><<<grid, 256, 0, st>>>(a);
+  } else {
+    dim3 grid((unsigned)groups, a.C / 8, a.N);
+    norm_bwd_b_kernel<1><<<grid, 256, 0, st>>>(a);
+  }
   SEUNET_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
