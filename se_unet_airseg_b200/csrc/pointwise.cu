@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256, SPLIT == 2 ? 4 : (C == 64 ? 3 : (C == 32 
   const int tvox = SPLIT == 2 ? (threadIdx.x & 15) | ((threadIdx.x >> 5) << 4) : threadIdx.x;
   constexpr int VPB = 256 / SPLIT;
   const int k0 = sub * KPT;
-#pragma unroll 1
+#pragma unroll 1     // (unrolled x2 / x4 for the 16- / 8-channel instances, round 2 late: ec2 24.9 -> 26.1 us, dc6 17.6 -> 18.4, ec1 unchanged)
   for (int u = 0; u < VPT; ++u) {
     const long long v = (blockIdx.x * (long long)VPT + u) * VPB + tvox;
     if (v >= a.V) break;                    // (V is a multiple of 32: both lanes of a pair leave together)
