@@ -168,3 +168,35 @@ def test_reference_training_loop_runs_unchanged_on_the_drop_in_module():
         a0, a1 = model(x)
         b0, b1 = fresh(x)
     assert torch.equal(a1, b1) and torch.equal(a0, b0)
+
+
+def test_graph_mode_step_equals_eager_step():
+    """DataParallelTrainer(graph=True) replays forward + losses + backward as one CUDA graph: same kernels on static copies of
+    the inputs, so the trajectory equals the eager one up to the order of the floating-point atomics; new inputs, new DropLayer
+    draws and the changing AdamW step number must all reach the replayed step (train.py:428-440 feeds a new batch every step)."""
+    from se_unet_airseg_b200 import SE_UNet
+    from se_unet_airseg_b200.trainer import DataParallelTrainer
+    sd = oracle.init_params(2, 1, seed=41)
+    shape = (2, 1, 16, 24, 16)
+    batches = []
+    for it in range(5):
+        g = torch.Generator().manual_seed(50 + it)
+        x = torch.rand(2, 2, 16, 24, 16, generator=g).cuda()
+        batches.append((x,) + tuple(t.cuda() for t in _targets(shape, 60 + it)))
+    runs = []
+    for graph in (False, True):
+        m = SE_UNet(2, 1)
+        m.load_state_dict(sd)
+        m = m.cuda().train()
+        tr = DataParallelTrainer(m, stage=3, graph=graph)
+        losses = []
+        for it, b in enumerate(batches):
+            torch.manual_seed(200 + it)           # the DropLayer draws come from the CPU generator
+            losses.append(tr.step(*b).item())
+        runs.append((losses, tr.flat.clone(), tr))
+    (la, pa, _), (lb, pb, trb) = runs
+    assert trb._graphs and all(g["graph"] is not None for g in trb._graphs.values())    # steps 3.. were replays
+    assert all(abs(a - b) <= 2e-5 for a, b in zip(la, lb)), (la, lb)
+    assert len(set(round(v, 6) for v in lb)) == len(lb)                               # every step saw its own batch
+    d = (pa - pb).abs()
+    assert d.max().item() <= 5 * 2 * 1e-4 + 1e-6 and d.mean().item() <= 1e-5           # see the AdamW remark in the test above

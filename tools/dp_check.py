@@ -19,12 +19,12 @@ weight = torch.where(label > 0, torch.rand(B, 1, S, S, S, generator=g) * 2 + 0.5
 skel = label * (torch.rand(B, 1, S, S, S, generator=g) > 0.5).float()
 sd = oracle.init_params(2, 1, seed=3)
 
-def run(trainer_world, tensors):
+def run(trainer_world, tensors, graph=False, steps=2):
     m = SE_UNet(2, 1); m.load_state_dict(sd); m = m.to(dev).eval()
-    tr = DataParallelTrainer(m, stage=3)
+    tr = DataParallelTrainer(m, stage=3, graph=graph)
     tr.world = trainer_world
     losses, g1 = [], None
-    for it in range(2):
+    for it in range(steps):
         losses.append(tr.step(*tensors).item())
         if it == 0:
             g1 = tr.grads.clone()      # identical parameters on both sides only at the first step
@@ -32,6 +32,9 @@ def run(trainer_world, tensors):
 
 shard = [t.chunk(world)[rank].contiguous().to(dev) for t in (x, label, weight, skel)]
 p_dp, g_dp, l_dp = run(world, shard)
+# the same two-rank step replayed as a CUDA graph (both NCCL exchanges captured): steps 3 and 4 are replays
+p_gr, _, l_gr = run(world, shard, graph=True, steps=4)
+p_e4, _, l_e4 = run(world, shard, graph=False, steps=4)
 if rank == 0:
     full = [t.to(dev) for t in (x, label, weight, skel)]
     p_1, g_1, l_1 = run(1, full)
@@ -39,6 +42,9 @@ if rank == 0:
     d = (p_dp - p_1).abs()
     print(f"world={world}: losses dp {l_dp} vs single {l_1}; first-step grad rel err {gerr:.3e}; param diff mean {d.mean().item():.3e} max {d.max().item():.3e}")
     assert abs(l_dp[0] - l_1[0]) < 1e-5 and gerr < 1e-2
+    dg = (p_gr - p_e4).abs()
+    print(f"graph mode: losses {l_gr} vs eager {l_e4}; param diff mean {dg.mean().item():.3e} max {dg.max().item():.3e}")
+    assert all(abs(a - b) < 2e-5 for a, b in zip(l_gr, l_e4)) and dg.mean().item() < 1e-5
     print("DP CHECK OK")
 dist.barrier()
 dist.destroy_process_group()
