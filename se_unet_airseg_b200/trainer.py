@@ -43,6 +43,8 @@ def loss_from_sums(stage, sums):
 
 class DataParallelTrainer:
     def __init__(self, model, stage=2, graph=False, **adamw):
+        """stage: 1 | 2 | 3 (train.py's curriculum: Dice; LIB-weighted union loss; + skeleton term).  graph: replay the step as
+        one CUDA graph per input shape (see the module docstring).  adamw: lr / betas / eps / weight_decay overrides."""
         self.model, self.stage = model, stage
         self.graph_mode = bool(graph)
         self._graphs = {}
@@ -175,6 +177,8 @@ class DataParallelTrainer:
             mk = lambda t: None if t is None else torch.empty_like(t, memory_format=torch.contiguous_format)
             g = dict(x=mk(x), label=mk(label), weight=mk(weight), skel=mk(skel), drop0=mk(drop0), drop1=mk(drop1), graph=None, warm=0,
                      plan=plan)             # (the reference keeps the plan's workspace alive if the module's plan cache evicts it)
+            while len(self._graphs) >= 4:   # a graph pins its static inputs and its plan's workspace: keep the last few shapes
+                self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = g
         for name, src in (("x", x), ("label", label), ("weight", weight), ("skel", skel), ("drop0", drop0), ("drop1", drop1)):
             if src is not None:
