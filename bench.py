@@ -348,7 +348,10 @@ def run_ours(args):
                     "loss": float(loss_t.item()), "tflops": flop_patch * global_batch / (ms_t * 1e-3) / 1e12}
 
         def time_train_guarded(*a):
-            # the secondary metric must never cost the headline line: a failed graph capture falls back to the eager step
+            # the secondary metric must never cost the headline line: a failed graph capture falls back to the eager step, and
+            # the capture with NCCL inside was only verified on 1, 2 and 4 GPUs in this round (GPU budget) - 8 ranks run eagerly
+            if world > 4:
+                return time_train(*a, graph=False)
             try:
                 return time_train(*a, graph=True)
             except Exception as e:          # noqa: BLE001
